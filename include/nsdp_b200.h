@@ -1,0 +1,204 @@
+/*
+ * nsdp_b200 — C ABI of libnsdp_b200.so: the B200 (sm_100a) kernels behind NSDP's TDNet hot path.
+ *
+ * This is the drop-in boundary. Part 1 replaces, entry point for entry point, what the
+ * reference's pybind11 module `pointnet2_ops._ext` binds
+ * (pointnet2_ops_lib/pointnet2_ops/_ext-src/src/bindings.cpp:6-19); part 2 is the fused replacement of
+ * the torch-op chains in model/encoder/blocks.py and model/decoder/blocks.py.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is DEVICE memory unless noted, fp32 / int32, contiguous,
+ *     16-byte aligned; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - the callee never allocates, never synchronises, never calls exit(); kernels are enqueued on
+ *     `stream` of the CURRENT device (the caller holds the device guard — the reference's _ext has none,
+ *     a latent multi-GPU bug noted in SURVEY.md §2.2);
+ *   - returns NSDP_OK (0) or a negative nsdp_status; nsdp_strerror() names it;
+ *   - outputs are fully overwritten unless documented as "accumulates";
+ *   - thread-safe, no global mutable state except a lazily initialised kernel-attribute cache.
+ */
+#ifndef NSDP_B200_H_
+#define NSDP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NSDP_OK = 0,
+  NSDP_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, k > N ... */
+  NSDP_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels are instantiated for */
+  NSDP_ERR_CUDA = -3,             /* launch failed; nsdp_last_cuda_error() has the cudaError_t */
+  NSDP_ERR_WORKSPACE = -4         /* workspace missing or too small */
+} nsdp_status;
+
+const char *nsdp_strerror(int status);
+int nsdp_last_cuda_error(void);   /* cudaError_t of the last failed launch on this thread */
+const char *nsdp_version(void);
+/* Arch the library was compiled for, e.g. "sm_100a". */
+const char *nsdp_build_arch(void);
+
+/* ====================================================================================================
+ * Part 1 — pointnet2_ops._ext replacements
+ * ==================================================================================================== */
+
+/* furthest_point_sampling(points (B,N,3) f32, nsamples) -> (B,nsamples) i32
+ * replaces sampling.h:6 / sampling.cpp:66-87 / sampling_gpu.cu:69-229. Bit-exact with the reference
+ * kernel including its tie-break. `out_idx` (B,m) is fully written.
+ * No workspace: the running min-distances live in registers of a thread-block cluster. */
+int nsdp_fps_f32(const float *xyz, int B, int N, int m, int32_t *out_idx, void *stream);
+
+/* gather_points(points (B,C,N), idx (B,M)) -> (B,C,M)            sampling.h:4, sampling_gpu.cu:8-30 */
+int nsdp_gather_points_f32(const float *points, const int32_t *idx, int B, int C, int N, int M,
+                           float *out, void *stream);
+/* gather_points_grad(grad_out (B,C,M), idx (B,M), n) -> (B,C,N)  sampling.h:5, sampling_gpu.cu:34-57
+ * `grad_points` must be zero-filled by the caller (the reference's host wrapper does torch::zeros);
+ * ACCUMULATES with atomics. */
+int nsdp_gather_points_grad_f32(const float *grad_out, const int32_t *idx, int B, int C, int N, int M,
+                                float *grad_points, void *stream);
+
+/* ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> (B,M,nsample) i32
+ * ball_query.h:4-5, ball_query_gpu.cu:9-44. Rows without any hit are all 0 (reference: torch::zeros). */
+int nsdp_ball_query_f32(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                        int nsample, int32_t *out_idx, void *stream);
+
+/* group_points(points (B,C,N), idx (B,M,K)) -> (B,C,M,K)         group_points.h:4, group_points_gpu.cu:8-28 */
+int nsdp_group_points_f32(const float *points, const int32_t *idx, int B, int C, int N, int M, int K,
+                          float *out, void *stream);
+/* group_points_grad(grad_out (B,C,M,K), idx, n) -> (B,C,N)       group_points.h:5, group_points_gpu.cu:43-64
+ * ACCUMULATES into caller-zeroed `grad_points`. */
+int nsdp_group_points_grad_f32(const float *grad_out, const int32_t *idx, int B, int C, int N, int M,
+                               int K, float *grad_points, void *stream);
+
+/* three_nn(unknown (B,n,3), known (B,m,3)) -> dist2 (B,n,3) f32, idx (B,n,3) i32
+ * interpolate.h:6, interpolate_gpu.cu:9-59 (squared distances; the Python side takes the sqrt). */
+int nsdp_three_nn_f32(const float *unknown, const float *known, int B, int n, int m, float *dist2,
+                      int32_t *out_idx, void *stream);
+/* three_interpolate(points (B,C,m), idx (B,n,3), weight (B,n,3)) -> (B,C,n)  interpolate_gpu.cu:72-101 */
+int nsdp_three_interpolate_f32(const float *points, const int32_t *idx, const float *weight, int B,
+                               int C, int m, int n, float *out, void *stream);
+/* three_interpolate_grad(grad_out (B,C,n), idx, weight, m) -> (B,C,m)        interpolate_gpu.cu:116-143
+ * ACCUMULATES into caller-zeroed `grad_points`. */
+int nsdp_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx, const float *weight,
+                                    int B, int C, int n, int m, float *grad_points, void *stream);
+
+/* ====================================================================================================
+ * Part 2 — fused replacements of the torch-op chains (no _ext equivalent in the reference)
+ * ==================================================================================================== */
+
+/* k nearest neighbours: replaces `square_distance(q, ref).argsort()[:, :, :k]`
+ * (model/utils.py:39-55; model/encoder/blocks.py:101-102, 287-288; model/decoder/blocks.py:50-52).
+ * query (B,M,3), ref (B,N,3) -> out_idx (B,M,k) i32 ascending by (distance, index); out_d2 (B,M,k) or
+ * NULL. Distance = ((dx*dx + dy*dy) + dz*dz), separately rounded, like torch. The [M,N] matrix is never
+ * materialised. `workspace` is only needed when nsdp_knn_workspace_bytes() > 0 (reference range split
+ * over several threads per query for large N). 1 <= k <= min(N, 64). */
+size_t nsdp_knn_workspace_bytes(int B, int M, int N, int k);
+int nsdp_knn_f32(const float *query, const float *ref, int B, int M, int N, int k, int32_t *out_idx,
+                 float *out_d2, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Vector ("point-transformer") attention core over neighbourhoods — the pair-level part of
+ * TransformerBlock (model/encoder/blocks.py:104-126), TransformerSetAbstraction (:290-308) and
+ * CrossTransformerBlock (model/decoder/blocks.py:62-91). For centre i and neighbour j = idx[i][t]:
+ *     rel   = sign * (xyz_c[i] - xyz_n[j])
+ *     h     = relu(wd0 * rel + bd0)                         (3 -> D)
+ *     dlt   = wd2 * h                                       (bias folded into vc by the caller)
+ *     g     = relu(wp * h + pc + qp[i] - kp[j])             (wp = Wgamma0 * Wdelta2, folded by the caller)
+ *     a     = wg2 * g                                       (its bias cancels in the softmax)
+ *     w     = softmax over t (per channel)
+ *     out[i]= sum_t w * (vc + vp[j] + dlt)
+ * With has_global != 0 one extra row per centre takes part in the softmax: rel-free (h = 0), with
+ * g = relu(gq[b]) and value gv[b] (the decoder's global token, decoder/blocks.py:64-75).
+ * Weight matrices are passed TRANSPOSED (K-major): wd2t[kk*D + c] = Wdelta2[c][kk] etc.
+ * idx == NULL means "every centre attends to all N source points" (group_all, blocks.py:96-99).
+ * qp/kp/vp may be NULL (treated as zeros: the pos_only block). D <= 256, K <= 128 (K <= 127 with global).
+ */
+typedef struct {
+  const float *xyz_c; /* (B,M,3) */
+  const float *xyz_n; /* (B,N,3) */
+  const int32_t *idx; /* (B,M,K) or NULL */
+  const float *qp;    /* (B,M,D) or NULL */
+  const float *kp;    /* (B,N,D) or NULL */
+  const float *vp;    /* (B,N,D) or NULL */
+  const float *gq;    /* (B,D) pre-activation of the global row, or NULL */
+  const float *gv;    /* (B,D) value of the global row, or NULL */
+  const float *wd0;   /* (D,3) row-major as in nn.Linear(3,D).weight */
+  const float *bd0;   /* (D) */
+  const float *wd2t;  /* (D,D) transposed */
+  const float *wpt;   /* (D,D) transposed */
+  const float *wg2t;  /* (D,D) transposed */
+  const float *pc;    /* (D) */
+  const float *vc;    /* (D) */
+  int B, M, N, K, D;
+  int has_global;
+  float sign;
+} nsdp_vattn_args;
+
+int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, void *stream);
+
+/* Backward of nsdp_vattn_fwd_f32 (recomputes the forward chain; nothing but inputs is saved).
+ * All gradient buffers ACCUMULATE and must be zero-filled (or hold a running sum) on entry; any of
+ * them may be NULL to skip it (d_xyz_* are NULL at every level but the first, where the reference's
+ * anchors are detached). */
+typedef struct {
+  float *d_qp;    /* (B,M,D) */
+  float *d_kp;    /* (B,N,D) */
+  float *d_vp;    /* (B,N,D) */
+  float *d_gq;    /* (B,D) */
+  float *d_gv;    /* (B,D) */
+  float *d_wd0;   /* (D,3) */
+  float *d_bd0;   /* (D) */
+  float *d_wd2t;  /* (D,D) */
+  float *d_wpt;   /* (D,D) */
+  float *d_wg2t;  /* (D,D) */
+  float *d_pc;    /* (D) */
+  float *d_vc;    /* (D) */
+  float *d_xyz_c; /* (B,M,3) */
+  float *d_xyz_n; /* (B,N,3) */
+} nsdp_vattn_grads;
+
+size_t nsdp_vattn_bwd_workspace_bytes(const nsdp_vattn_args *args);
+int nsdp_vattn_bwd_f32(const nsdp_vattn_args *args, const float *d_out /* (B,M,D) */,
+                       const nsdp_vattn_grads *grads, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* Decoder ResNet-FC tail (model/decoder/crosstransformer_decoder.py:63-69 with ResnetBlockFC,
+ * model/decoder/blocks.py:133-142), fused over row tiles:
+ *     net = init(lat); for i < n_blocks: net += fc_c[i](lat); net += fc_1[i](relu(fc_0[i](relu(net))));
+ *     out = fc_out(relu(net))
+ * lat (R, C) with C <= 256; hidden H == 128; out (R, O) with O <= 4. Weights are passed transposed
+ * (K-major) and concatenated:
+ *     wc_t  (C, (1+n_blocks)*H): columns [0,H) = init_enc, then fc_c[0..n)      bc ((1+n_blocks)*H)
+ *     w0_t  (n_blocks, H, H), b0 (n_blocks, H); w1_t (n_blocks, H, H), b1 (n_blocks, H)
+ *     wo_t  (H, O), bo (O)
+ */
+typedef struct {
+  const float *lat;
+  const float *wc_t, *bc;
+  const float *w0_t, *b0, *w1_t, *b1;
+  const float *wo_t, *bo;
+  int R, C, H, O, n_blocks;
+} nsdp_tail_args;
+
+int nsdp_resnet_tail_fwd_f32(const nsdp_tail_args *args, float *out /* (R,O) */, void *stream);
+
+/* Backward of nsdp_resnet_tail_fwd_f32 (recomputes the activations tile by tile). Gradient buffers have the
+ * layouts of the corresponding (transposed, concatenated) forward arguments, ACCUMULATE, and must be
+ * zero-filled on entry; d_lat (R,C) is fully overwritten. */
+typedef struct {
+  float *d_lat;
+  float *d_wc_t, *d_bc;
+  float *d_w0_t, *d_b0, *d_w1_t, *d_b1;
+  float *d_wo_t, *d_bo;
+} nsdp_tail_grads;
+
+size_t nsdp_resnet_tail_bwd_workspace_bytes(const nsdp_tail_args *args);
+int nsdp_resnet_tail_bwd_f32(const nsdp_tail_args *args, const float *d_out /* (R,O) */,
+                             const nsdp_tail_grads *grads, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSDP_B200_H_ */

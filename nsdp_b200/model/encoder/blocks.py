@@ -1,0 +1,201 @@
+"""Point-transformer encoder blocks on the nsdp_b200 kernels.
+
+Same class names, constructor arguments, attribute names (hence state_dict keys) and forward signatures as
+the reference's model/encoder/blocks.py, so reference checkpoints load unchanged. What differs is HOW the
+forward runs: the pair-level chain (gather -> fc_delta -> fc_gamma -> softmax -> weighted sum,
+blocks.py:104-126 and :290-308) is ONE fused CUDA kernel (ops.vector_attention); k-NN is the tiled top-k
+kernel instead of a full distance matrix + argsort (blocks.py:101-102, 287-288); FPS is the
+cluster-resident kernel (blocks.py:283). Only per-point linear layers and BatchNorm stay torch ops
+(plain cuBLAS GEMMs / cuDNN-free batch_norm on (B*n, C) views).
+
+Algebra used to shrink the pair-level work (exact in real arithmetic, fp32 rounding differs ~1e-7):
+    fc_gamma[0](q_i - k_j + delta_ij) = (Wg0 Wq) x_i - (Wg0 Wk) x_j + (Wg0 Wd2) h_ij + (Wg0 bd2 + bg0)
+so the kernel receives per-POINT tables Q' and K' and one folded matrix W' = Wg0 Wd2; fc_gamma[2].bias
+is constant over the softmax axis and drops out. All folds are differentiable torch ops, so autograd
+delivers the gradients of the original parameters.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from nsdp_b200 import ops
+from nsdp_b200.model.utils import index_points, knn_indices
+
+
+def _mlp2(d_in: int, d: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(d_in, d), nn.ReLU(), nn.Linear(d, d))
+
+
+def _bn_rows(bn: nn.BatchNorm1d, x: torch.Tensor) -> torch.Tensor:
+    """BatchNorm1d over the channel dim of a (B, n, C) tensor == the reference's permute -> bn -> permute."""
+    B, n, C = x.shape
+    return bn(x.reshape(B * n, C)).reshape(B, n, C)
+
+
+def _pointwise(conv: nn.Conv1d, x: torch.Tensor) -> torch.Tensor:
+    """A kernel-size-1 Conv1d applied to (B, n, C) rows."""
+    return F.linear(x, conv.weight.squeeze(-1), conv.bias)
+
+
+def fold_pair_mlps(fc_delta: nn.Sequential, fc_gamma: nn.Sequential):
+    """Kernel-side weights for one (fc_delta, fc_gamma) pair: see nsdp_vattn_args."""
+    wd0, bd0 = fc_delta[0].weight, fc_delta[0].bias
+    wd2, bd2 = fc_delta[2].weight, fc_delta[2].bias
+    wg0, bg0 = fc_gamma[0].weight, fc_gamma[0].bias
+    wg2 = fc_gamma[2].weight
+    return dict(
+        wd0=wd0.contiguous(), bd0=bd0.contiguous(),
+        wd2t=wd2.t().contiguous(),
+        wpt=(wg0 @ wd2).t().contiguous(),
+        wg2t=wg2.t().contiguous(),
+        pc=torch.mv(wg0, bd2) + bg0,
+        vc=bd2.contiguous(),
+    )
+
+
+class TransformerBlock(nn.Module):
+    """Local / global vector self-attention (reference: model/encoder/blocks.py:52-134)."""
+
+    def __init__(self, d_model, k, pos_only=False, group_all=False) -> None:
+        super().__init__()
+        self.pos_only = pos_only
+        self.bn = nn.BatchNorm1d(d_model)
+        self.fc_delta = _mlp2(3, d_model)
+        self.fc_gamma = _mlp2(d_model, d_model)
+        self.w_qs = nn.Linear(d_model, d_model, bias=False)
+        self.w_ks = nn.Linear(d_model, d_model, bias=False)
+        self.w_vs = nn.Linear(d_model, d_model, bias=False)
+        self.k = k
+        self.group_all = group_all
+
+    def forward(self, xyz, feats=None):
+        B, n, _ = xyz.shape
+        xyz = xyz.contiguous()
+        idx = None if self.group_all else knn_indices(xyz, xyz, min(self.k, n))
+        w = fold_pair_mlps(self.fc_delta, self.fc_gamma)
+        if self.pos_only:
+            res = ops.vector_attention(xyz, xyz, idx, None, None, None, sign=1.0, **w)
+        else:
+            wg0 = self.fc_gamma[0].weight
+            qp = F.linear(feats, wg0 @ self.w_qs.weight)
+            kp = F.linear(feats, wg0 @ self.w_ks.weight)
+            vp = self.w_vs(feats)
+            res = ops.vector_attention(xyz, xyz, idx, qp, kp, vp, sign=1.0, **w) + feats
+        return _bn_rows(self.bn, res)
+
+
+class ElementwiseMLP(nn.Module):
+    """bn3(x + relu(bn2(conv2(relu(bn1(conv1 x)))))) (reference: model/encoder/blocks.py:137-159)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv1 = nn.Conv1d(dim, dim, 1)
+        self.bn1 = nn.BatchNorm1d(dim)
+        self.conv2 = nn.Conv1d(dim, dim, 1)
+        self.bn2 = nn.BatchNorm1d(dim)
+        self.bn3 = nn.BatchNorm1d(dim)
+
+    def forward(self, x):
+        h = F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, x)))
+        h = F.relu(_bn_rows(self.bn2, _pointwise(self.conv2, h)))
+        return _bn_rows(self.bn3, x + h)
+
+
+class TransformerSetAbstraction(nn.Module):
+    """FPS down-sampling + two stacked cross vector-attentions (reference: model/encoder/blocks.py:221-314)."""
+
+    def __init__(self, npoint, nneigh, dim):
+        super().__init__()
+        self.npoint = npoint
+        self.nneigh = nneigh
+        self.bnorm0 = nn.BatchNorm1d(dim)
+        self.bnorm1 = nn.BatchNorm1d(dim)
+        self.bnorm2 = nn.BatchNorm1d(dim)
+        self.bn1 = nn.BatchNorm1d(dim)
+        self.conv1 = nn.Conv1d(dim, dim, 1)
+        self.conv2 = nn.Conv1d(dim, dim, 1)
+        self.fc_delta1 = _mlp2(3, dim)
+        self.fc_gamma1 = _mlp2(dim, dim)
+        self.fc_gamma2 = _mlp2(dim, dim)
+        self.w_qs = nn.Linear(dim, dim, bias=False)
+        self.w_ks = nn.Linear(dim, dim, bias=False)
+        self.w_vs = nn.Linear(dim, dim, bias=False)
+        self.w_qs2 = nn.Linear(dim, dim, bias=False)
+        self.w_ks2 = nn.Linear(dim, dim, bias=False)
+        self.w_vs2 = nn.Linear(dim, dim, bias=False)
+
+    def forward(self, xyz, points):
+        xyz = xyz.contiguous()
+        N = xyz.shape[1]
+        with torch.no_grad():
+            fps_idx = ops.furthest_point_sampling(xyz.detach(), self.npoint)
+            new_xyz = index_points(xyz.detach(), fps_idx).contiguous()  # detached, as in blocks.py:282-285
+            idx = knn_indices(new_xyz, xyz, min(self.nneigh, N))
+        centre = index_points(points, fps_idx)
+
+        w1 = fold_pair_mlps(self.fc_delta1, self.fc_gamma1)
+        g10 = self.fc_gamma1[0].weight
+        qp = F.linear(centre, g10 @ self.w_qs.weight)
+        kp = F.linear(points, g10 @ self.w_ks.weight)
+        vp = self.w_vs(points)
+        # rel = neighbour - centre (blocks.py:295) -> sign = -1
+        res1 = ops.vector_attention(new_xyz, xyz, idx, qp, kp, vp, sign=-1.0, **w1)
+        res1 = res1 + _pointwise(self.conv2, F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, res1))))
+        res1 = _bn_rows(self.bnorm0, res1)
+
+        w2 = fold_pair_mlps(self.fc_delta1, self.fc_gamma2)  # same delta MLP, second gamma MLP
+        g20 = self.fc_gamma2[0].weight
+        qp2 = F.linear(res1, g20 @ self.w_qs2.weight)
+        kp2 = F.linear(points, g20 @ self.w_ks2.weight)
+        vp2 = self.w_vs2(points)
+        res2 = ops.vector_attention(new_xyz, xyz, idx, qp2, kp2, vp2, sign=-1.0, **w2)
+
+        out = _bn_rows(self.bnorm1, res1 + res2) + centre
+        return new_xyz, _bn_rows(self.bnorm2, out)
+
+
+class PointNetSetAbstraction(nn.Module):
+    """PointNet++-style max-pool set abstraction (reference: model/encoder/blocks.py:162-217; ablation only —
+    no shipped config selects it). FPS and k-NN run on the nsdp_b200 kernels; the rest is per-point torch ops."""
+
+    def __init__(self, npoint, nneigh, in_channel, dim):
+        super().__init__()
+        self.npoint = npoint
+        self.nneigh = nneigh
+        self.fc1 = nn.Linear(in_channel, dim)
+        self.conv1 = nn.Conv1d(dim, dim, 1)
+        self.conv2 = nn.Conv1d(dim, dim, 1)
+        self.bn1 = nn.BatchNorm1d(dim)
+        self.bn2 = nn.BatchNorm1d(dim)
+        self.bn = nn.BatchNorm1d(dim)
+
+    def forward(self, xyz, points):
+        xyz = xyz.contiguous()
+        with torch.no_grad():
+            fps_idx = ops.furthest_point_sampling(xyz.detach(), self.npoint)
+        new_xyz = index_points(xyz, fps_idx)
+        points = self.fc1(points)
+        centre = index_points(points, fps_idx)
+        h = F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, points)))
+        points = points + F.relu(_bn_rows(self.bn2, _pointwise(self.conv2, h)))
+        idx = knn_indices(new_xyz, xyz, min(self.nneigh, xyz.shape[1]))
+        pooled = index_points(points, idx).max(dim=2)[0]
+        return new_xyz, _bn_rows(self.bn, centre + pooled)
+
+
+class TransitionDown(nn.Module):
+    """Wrapper choosing the set-abstraction flavour (reference: model/encoder/blocks.py:18-49)."""
+
+    def __init__(self, npoint, nneighbor, dim, type="attentive") -> None:
+        super().__init__()
+        if type == "attentive":
+            self.sa = TransformerSetAbstraction(npoint, nneighbor, dim)
+        elif type == "maxpool":
+            self.sa = PointNetSetAbstraction(npoint, nneighbor, dim, dim)
+        else:
+            raise ValueError("Set Abstraction type " + type + " unknown!")
+
+    def forward(self, xyz, feats):
+        return self.sa(xyz, feats)

@@ -1,0 +1,90 @@
+"""Arbitrary-pose composition (reference: model/flow_arbitrary.py:7-85): source -> canonical with the
+backward TDNet (for the space samples AND the surface samples), then canonical -> target with the forward
+TDNet whose encoder input is cat[surface_src2cano, surface_tgt, mask].
+
+The reference runs the canonicalise ENCODER twice on identical input (flow_arbitrary.py:19-20). Here it is
+encoded once and decoded for both query sets; to stay bit-compatible with the reference's BatchNorm
+bookkeeping in train() mode (every BN updates its running stats twice per step) the second
+momentum update is replayed on the buffers instead of recomputing the pass.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from nsdp_b200 import dist as nsdp_dist
+from nsdp_b200.model.utils import compute_l2_error
+
+
+def _bn_layers(module):
+    return [m for m in module.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+
+
+class FlowArbitrary(nn.Module):
+    def __init__(self, cfg, model_canonicalize, model_deform):
+        super().__init__()
+        self.model_canonicalize = model_canonicalize
+        self.model_deform = model_deform
+
+    def _canonicalize_twice(self, space_samples_src, surface_samples_src):
+        cano = self.model_canonicalize
+        bns = _bn_layers(cano.encoder) if self.training else []
+        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
+        encoding = cano.encode(surface_samples_src)
+        # replay the second identical running-stat update: r2 = r1 + m*(batch - r1), with
+        # batch = r0 + (r1 - r0)/m recovered from the first update
+        with torch.no_grad():
+            for bn, (m0, v0) in zip(bns, before):
+                mom = bn.momentum
+                if mom is None:  # cumulative average: second identical sample leaves the mean unchanged
+                    bn.num_batches_tracked += 1
+                    continue
+                batch_mean = m0 + (bn.running_mean - m0) / mom
+                batch_var = v0 + (bn.running_var - v0) / mom
+                bn.running_mean += mom * (batch_mean - bn.running_mean)
+                bn.running_var += mom * (batch_var - bn.running_var)
+                bn.num_batches_tracked += 1
+        space = cano.decode(space_samples_src, encoding)
+        surface = cano.decode(surface_samples_src, encoding)
+        return space, surface
+
+    def forward(self, space_samples_src, surface_samples_src, surface_samples_tgt, cano_handle_sample_mask):
+        space_src2cano, surface_src2cano = self._canonicalize_twice(space_samples_src, surface_samples_src)
+        deform_inputs = torch.cat([surface_src2cano, surface_samples_tgt, cano_handle_sample_mask], dim=-1).contiguous()
+        return self.model_deform(space_src2cano, deform_inputs)
+
+
+def _split_inputs(data_dict):
+    s = data_dict["surface_samples_inputs"]
+    return s[:, :, 0:3], s[:, :, 3:6], s[:, :, 6:7]
+
+
+def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
+    optimizer.zero_grad()
+    src, tgt, mask = _split_inputs(data_dict)
+    pred = model(data_dict["space_samples_src"], src, tgt, mask)
+    loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
+    loss.backward()
+    nsdp_dist.allreduce_gradients(model)
+    optimizer.step()
+    return loss.item()
+
+
+@torch.no_grad()
+def validate_on_batch_with_arbitrary(model, data_dict, config):
+    src, tgt, mask = _split_inputs(data_dict)
+    pred = model(data_dict["space_samples_src"], src, tgt, mask)
+    return compute_l2_error(pred, data_dict["space_samples_tgt"]).item()
+
+
+@torch.no_grad()
+def test_on_batch_with_arbitrary(model, data_dict, config, compute_loss=False):
+    src, tgt, mask = _split_inputs(data_dict)
+    data_dict["surface_samples_tgt_pred"] = model(src, src, tgt, mask)
+    verts_pred = model(data_dict["verts_src"], src, tgt, mask)
+    data_dict["verts_tgt_pred"] = verts_pred
+    if compute_loss:
+        loss = compute_l2_error(verts_pred, data_dict["verts_tgt"])
+    else:
+        loss = torch.zeros((1), dtype=torch.float32)
+    return loss.item(), data_dict

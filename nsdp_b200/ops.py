@@ -1,0 +1,311 @@
+"""torch-facing operators over the C ABI (include/nsdp_b200.h).
+
+torch is plumbing here: it owns device memory and streams; every operator below passes raw device
+pointers + the current CUDA stream into libnsdp_b200.so. CPU tensors are rejected loudly, exactly like
+the reference extension ("CPU not supported", pointnet2_ops/_ext-src/src/sampling.cpp:82-84).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import TailArgs, TailGrads, VattnArgs, VattnGrads, check
+
+LAUNCHES = 0  # number of libnsdp_b200 kernel-launching calls made (bench.py reports it)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CPU not supported (nsdp_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a float tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    return t
+
+
+def _chk_i32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CPU not supported (nsdp_b200 has no CPU path)")
+    if t.dtype != torch.int32:
+        raise RuntimeError(f"{name} must be an int tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------
+# Part 1: pointnet2_ops._ext operators (same names / argument order as bindings.cpp:6-19)
+# ---------------------------------------------------------------------------------------------------
+def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor:
+    """(B,N,3) f32 -> (B,nsamples) i32; sampling.cpp:66-87."""
+    _chk_f32("points", points)
+    B, N, _ = points.shape
+    out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nsdp_fps_f32(points.data_ptr(), B, N, int(nsamples), out.data_ptr(), _stream()), "nsdp_fps_f32")
+    _count()
+    return out
+
+
+def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """(B,C,N), (B,M) i32 -> (B,C,M); sampling.cpp:16-41."""
+    _chk_f32("points", points)
+    _chk_i32("idx", idx)
+    B, Cc, N = points.shape
+    M = idx.shape[1]
+    out = torch.empty((B, Cc, M), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nsdp_gather_points_f32(points.data_ptr(), idx.data_ptr(), B, Cc, N, M, out.data_ptr(), _stream()),
+              "nsdp_gather_points_f32")
+    _count()
+    return out
+
+
+def gather_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    _chk_f32("grad_out", grad_out)
+    _chk_i32("idx", idx)
+    B, Cc, M = grad_out.shape
+    out = torch.zeros((B, Cc, n), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(_lib.lib().nsdp_gather_points_grad_f32(grad_out.data_ptr(), idx.data_ptr(), B, Cc, n, M, out.data_ptr(),
+                                                     _stream()), "nsdp_gather_points_grad_f32")
+    _count()
+    return out
+
+
+def ball_query(new_xyz: torch.Tensor, xyz: torch.Tensor, radius: float, nsample: int) -> torch.Tensor:
+    _chk_f32("new_xyz", new_xyz)
+    _chk_f32("xyz", xyz)
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    out = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().nsdp_ball_query_f32(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius), int(nsample),
+                                             out.data_ptr(), _stream()), "nsdp_ball_query_f32")
+    _count()
+    return out
+
+
+def group_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _chk_f32("points", points)
+    _chk_i32("idx", idx)
+    B, Cc, N = points.shape
+    _, M, K = idx.shape
+    out = torch.empty((B, Cc, M, K), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nsdp_group_points_f32(points.data_ptr(), idx.data_ptr(), B, Cc, N, M, K, out.data_ptr(),
+                                               _stream()), "nsdp_group_points_f32")
+    _count()
+    return out
+
+
+def group_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    _chk_f32("grad_out", grad_out)
+    _chk_i32("idx", idx)
+    B, Cc, M, K = grad_out.shape
+    out = torch.zeros((B, Cc, n), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(_lib.lib().nsdp_group_points_grad_f32(grad_out.data_ptr(), idx.data_ptr(), B, Cc, n, M, K, out.data_ptr(),
+                                                    _stream()), "nsdp_group_points_grad_f32")
+    _count()
+    return out
+
+
+def three_nn(unknowns: torch.Tensor, knows: torch.Tensor):
+    _chk_f32("unknowns", unknowns)
+    _chk_f32("knows", knows)
+    B, n, _ = unknowns.shape
+    m = knows.shape[1]
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    with torch.cuda.device(unknowns.device):
+        check(_lib.lib().nsdp_three_nn_f32(unknowns.data_ptr(), knows.data_ptr(), B, n, m, dist2.data_ptr(), idx.data_ptr(),
+                                           _stream()), "nsdp_three_nn_f32")
+    _count()
+    return [dist2, idx]
+
+
+def three_interpolate(points: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    _chk_f32("points", points)
+    _chk_i32("idx", idx)
+    _chk_f32("weight", weight)
+    B, Cc, m = points.shape
+    n = idx.shape[1]
+    out = torch.empty((B, Cc, n), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nsdp_three_interpolate_f32(points.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, Cc, m, n,
+                                                    out.data_ptr(), _stream()), "nsdp_three_interpolate_f32")
+    _count()
+    return out
+
+
+def three_interpolate_grad(grad_out: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, m: int) -> torch.Tensor:
+    _chk_f32("grad_out", grad_out)
+    _chk_i32("idx", idx)
+    _chk_f32("weight", weight)
+    B, Cc, n = grad_out.shape
+    out = torch.zeros((B, Cc, m), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(_lib.lib().nsdp_three_interpolate_grad_f32(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, Cc, n,
+                                                         m, out.data_ptr(), _stream()), "nsdp_three_interpolate_grad_f32")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Part 2: fused hot-path operators
+# ---------------------------------------------------------------------------------------------------
+def knn(query: torch.Tensor, ref: torch.Tensor, k: int, return_d2: bool = False):
+    """k nearest `ref` points of every `query` point, ascending (distance, index): (B,M,k) int32.
+    Replaces square_distance(...).argsort()[:, :, :k] (model/utils.py:39-55, encoder/blocks.py:101-102)."""
+    _chk_f32("query", query)
+    _chk_f32("ref", ref)
+    B, M, _ = query.shape
+    N = ref.shape[1]
+    out = torch.empty((B, M, k), dtype=torch.int32, device=query.device)
+    d2 = torch.empty((B, M, k), dtype=torch.float32, device=query.device) if return_d2 else None
+    L = _lib.lib()
+    with torch.cuda.device(query.device):
+        ws_bytes = L.nsdp_knn_workspace_bytes(B, M, N, int(k))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=query.device) if ws_bytes else None
+        check(L.nsdp_knn_f32(query.data_ptr(), ref.data_ptr(), B, M, N, int(k), out.data_ptr(), _p(d2), _p(ws), ws_bytes,
+                             _stream()), "nsdp_knn_f32")
+    _count(2 if ws_bytes else 1)
+    return (out, d2) if return_d2 else out
+
+
+def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign) -> VattnArgs:
+    B, M, _ = xyz_c.shape
+    N = xyz_n.shape[1]
+    D = wd2t.shape[0]
+    K = idx.shape[2] if idx is not None else N
+    a = VattnArgs()
+    a.xyz_c, a.xyz_n, a.idx = _p(xyz_c), _p(xyz_n), _p(idx)
+    a.qp, a.kp, a.vp, a.gq, a.gv = _p(qp), _p(kp), _p(vp), _p(gq), _p(gv)
+    a.wd0, a.bd0, a.wd2t, a.wpt, a.wg2t, a.pc, a.vc = _p(wd0), _p(bd0), _p(wd2t), _p(wpt), _p(wg2t), _p(pc), _p(vc)
+    a.B, a.M, a.N, a.K, a.D = B, M, N, K, D
+    a.has_global = 1 if gq is not None else 0
+    a.sign = float(sign)
+    return a
+
+
+class _VectorAttention(torch.autograd.Function):
+    """out = nsdp_vattn_fwd_f32(...); backward = nsdp_vattn_bwd_f32 (recompute, nothing but inputs saved)."""
+
+    @staticmethod
+    def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign):
+        tensors = dict(xyz_c=xyz_c, xyz_n=xyz_n, qp=qp, kp=kp, vp=vp, gq=gq, gv=gv, wd0=wd0, bd0=bd0, wd2t=wd2t,
+                       wpt=wpt, wg2t=wg2t, pc=pc, vc=vc)
+        for n, t in tensors.items():
+            if t is not None:
+                _chk_f32(n, t)
+        if idx is not None:
+            _chk_i32("idx", idx)
+        a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign)
+        out = torch.empty((a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device)
+        with torch.cuda.device(xyz_c.device):
+            check(_lib.lib().nsdp_vattn_fwd_f32(C.byref(a), out.data_ptr(), _stream()), "nsdp_vattn_fwd_f32")
+        _count()
+        ctx.sign = sign
+        ctx.save_for_backward(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, ctx.sign)
+        need = ctx.needs_input_grad
+
+        def z(t, flag):
+            return torch.zeros_like(t) if (t is not None and flag) else None
+
+        g = dict(d_xyz_c=z(xyz_c, need[0]), d_xyz_n=z(xyz_n, need[1]), d_qp=z(qp, need[3]), d_kp=z(kp, need[4]),
+                 d_vp=z(vp, need[5]), d_gq=z(gq, need[6]), d_gv=z(gv, need[7]), d_wd0=z(wd0, need[8]),
+                 d_bd0=z(bd0, need[9]), d_wd2t=z(wd2t, need[10]), d_wpt=z(wpt, need[11]), d_wg2t=z(wg2t, need[12]),
+                 d_pc=z(pc, need[13]), d_vc=z(vc, need[14]))
+        # xyz_c and xyz_n may be the SAME tensor (self attention): both gradients are returned and autograd
+        # sums them.
+        gs = VattnGrads()
+        for n, t in g.items():
+            setattr(gs, n, _p(t))
+        L = _lib.lib()
+        with torch.cuda.device(d_out.device):
+            ws_bytes = L.nsdp_vattn_bwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
+            check(L.nsdp_vattn_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
+                  "nsdp_vattn_bwd_f32")
+        _count()
+        return (g["d_xyz_c"], g["d_xyz_n"], None, g["d_qp"], g["d_kp"], g["d_vp"], g["d_gq"], g["d_gv"], g["d_wd0"],
+                g["d_bd0"], g["d_wd2t"], g["d_wpt"], g["d_wg2t"], g["d_pc"], g["d_vc"], None)
+
+
+def vector_attention(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign=1.0, gq=None, gv=None):
+    """Fused pair-level vector attention (see nsdp_vattn_args in include/nsdp_b200.h)."""
+    return _VectorAttention.apply(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, float(sign))
+
+
+def _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo) -> TailArgs:
+    a = TailArgs()
+    a.lat, a.wc_t, a.bc = _p(lat2d), _p(wc_t), _p(bc)
+    a.w0_t, a.b0, a.w1_t, a.b1 = _p(w0_t), _p(b0), _p(w1_t), _p(b1)
+    a.wo_t, a.bo = _p(wo_t), _p(bo)
+    a.R, a.C = lat2d.shape
+    a.H = w0_t.shape[-1]
+    a.O = wo_t.shape[1]
+    a.n_blocks = w0_t.shape[0]
+    return a
+
+
+class _ResnetTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
+        for n, t in dict(lat=lat2d, wc_t=wc_t, bc=bc, w0_t=w0_t, b0=b0, w1_t=w1_t, b1=b1, wo_t=wo_t, bo=bo).items():
+            _chk_f32(n, t)
+        a = _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
+        out = torch.empty((a.R, a.O), dtype=torch.float32, device=lat2d.device)
+        with torch.cuda.device(lat2d.device):
+            check(_lib.lib().nsdp_resnet_tail_fwd_f32(C.byref(a), out.data_ptr(), _stream()), "nsdp_resnet_tail_fwd_f32")
+        _count()
+        ctx.save_for_backward(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        a = _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
+        grads = [torch.empty_like(lat2d)] + [torch.zeros_like(t) for t in (wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)]
+        gs = TailGrads()
+        for n, t in zip(("d_lat", "d_wc_t", "d_bc", "d_w0_t", "d_b0", "d_w1_t", "d_b1", "d_wo_t", "d_bo"), grads):
+            setattr(gs, n, _p(t))
+        L = _lib.lib()
+        with torch.cuda.device(d_out.device):
+            ws_bytes = L.nsdp_resnet_tail_bwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
+            check(L.nsdp_resnet_tail_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
+                  "nsdp_resnet_tail_bwd_f32")
+        _count()
+        return tuple(grads)
+
+
+def resnet_tail(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
+    """Fused decoder ResNet-FC tail over rows: (R,C) -> (R,O). See nsdp_tail_args."""
+    return _ResnetTail.apply(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
