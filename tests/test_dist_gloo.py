@@ -1,0 +1,69 @@
+"""N>1 host logic on CPU: world_size-2 gloo. Checks that the flat gradient all-reduce averages across ranks
+(including parameters that received no gradient on some rank), that replicas are synchronised by
+broadcast_parameters, and the contiguous batch sharding."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from nsdp_b200 import dist as nd
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                      # replicas start DIFFERENT ...
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2, bias=False), torch.nn.Linear(2, 2))
+    nd.broadcast_parameters(model)                     # ... and are made identical
+    w0 = model[0].weight.detach().clone()
+    data = {"x": torch.arange(8 * 4, dtype=torch.float32).reshape(8, 4), "tag": "keep"}
+    shard = nd.shard_batch(data)
+    # the last layer is unused -> its grads stay None on every rank (like the pos_only block's q/k/v weights)
+    loss = model[1](model[0](shard["x"])).pow(2).mean()
+    loss.backward()
+    local = model[0].weight.grad.clone()
+    nd.allreduce_gradients(model)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    td.all_gather(gathered, local)
+    q.put((rank, w0, shard["x"][:, 0].tolist(), shard["tag"], model[0].weight.grad.clone(), sum(gathered) / world,
+           model[2].weight.grad.clone()))
+    td.destroy_process_group()
+
+
+def test_dp_allreduce_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, w0a, x0, tag0, g0, mean0, unused0), (r1, w0b, x1, tag1, g1, mean1, unused1) = res
+    assert torch.equal(w0a, w0b)                                   # broadcast made replicas identical
+    assert x0 == [0.0, 4.0, 8.0, 12.0] and x1 == [16.0, 20.0, 24.0, 28.0] and tag0 == "keep"
+    torch.testing.assert_close(g0, mean0)
+    torch.testing.assert_close(g0, g1)                             # every rank holds the averaged gradient
+    assert torch.count_nonzero(unused0) == 0 and torch.count_nonzero(unused1) == 0
+
+
+def test_inactive_without_process_group():
+    model = torch.nn.Linear(2, 2)
+    model(torch.ones(1, 2)).sum().backward()
+    g = model.weight.grad.clone()
+    nd.allreduce_gradients(model)                                  # no-op
+    assert torch.equal(g, model.weight.grad)
+    assert nd.shard_batch({"x": torch.zeros(4, 1)})["x"].shape[0] == 4
+    with pytest.raises(ValueError):
+        nd.shard_batch({"x": torch.zeros(5, 1)}, rank=0, world=2)

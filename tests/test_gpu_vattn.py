@@ -1,0 +1,111 @@
+"""GPU parity of the fused vector-attention and ResNet-FC tail kernels (through the C ABI) against a float64
+torch restatement of the math documented in include/nsdp_b200.h."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from nsdp_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def vattn_reference(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, gq=None, gv=None):
+    """float64 restatement of nsdp_vattn_fwd_f32."""
+    f = lambda t: None if t is None else t.double().cpu()
+    xyz_c, xyz_n, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, gq, gv = map(
+        f, (xyz_c, xyz_n, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, gq, gv))
+    B, M, _ = xyz_c.shape
+    N = xyz_n.shape[1]
+    D = wd2t.shape[0]
+    if idx is None:
+        idx = torch.arange(N).view(1, 1, N).expand(B, M, N)
+    idx = idx.long().cpu()
+    K = idx.shape[2]
+    gather = lambda t: torch.gather(t, 1, idx.reshape(B, M * K, 1).expand(-1, -1, t.shape[-1])).reshape(B, M, K, -1)
+    rel = sign * (xyz_c[:, :, None] - gather(xyz_n))
+    h = F.relu(rel @ wd0.t() + bd0)
+    dlt = h @ wd2t
+    pre = h @ wpt + pc
+    if qp is not None:
+        pre = pre + qp[:, :, None]
+    if kp is not None:
+        pre = pre - gather(kp)
+    a = F.relu(pre) @ wg2t
+    val = vc + dlt
+    if vp is not None:
+        val = val + gather(vp)
+    if gq is not None:
+        a = torch.cat([a, (F.relu(gq) @ wg2t)[:, None, None, :].expand(-1, M, -1, -1)], dim=2)
+        val = torch.cat([val, gv[:, None, None, :].expand(-1, M, -1, -1)], dim=2)
+    w = torch.softmax(a, dim=2)
+    return (w * val).sum(dim=2)
+
+
+def _rand_case(B, M, N, K, D, pos_only=False, has_global=False, group_all=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    xyz_n = r(B, N, 3) * 0.3
+    xyz_c = xyz_n[:, :M].clone() if M <= N else r(B, M, 3) * 0.3
+    idx = None if group_all else torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32)
+    sc = 1.0 / np.sqrt(D)
+    case = dict(xyz_c=xyz_c, xyz_n=xyz_n, idx=idx,
+                qp=None if pos_only else r(B, M, D) * 0.5, kp=None if pos_only else r(B, N, D) * 0.5,
+                vp=None if pos_only else r(B, N, D),
+                wd0=r(D, 3), bd0=r(D) * 0.1, wd2t=r(D, D) * sc, wpt=r(D, D) * sc, wg2t=r(D, D) * sc,
+                pc=r(D) * 0.1, vc=r(D) * 0.1)
+    if has_global:
+        case["gq"] = r(B, D)
+        case["gv"] = r(B, D)
+    return case
+
+
+CASES = [
+    dict(B=2, M=333, N=333, K=10, D=120),                       # transformer_begin
+    dict(B=2, M=50, N=400, K=16, D=120),                        # TSA level 0
+    dict(B=2, M=100, N=100, K=16, D=256),                       # transformer_downs.1
+    dict(B=2, M=100, N=100, K=100, D=256, group_all=True),      # full attention over the anchors
+    dict(B=2, M=777, N=100, K=7, D=200, has_global=True),       # decoder cross attention
+    dict(B=1, M=129, N=129, K=10, D=120, pos_only=True),        # backward net's first block
+    dict(B=1, M=5, N=9, K=3, D=64),                             # odd small
+    dict(B=1, M=40, N=40, K=40, D=128, group_all=True),
+]
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_vattn_forward(cfg, sign):
+    case = _rand_case(**cfg)
+    dev = {k: (v.to(DEV).contiguous() if torch.is_tensor(v) else v) for k, v in case.items()}
+    got = ops.vector_attention(sign=sign, **dev).cpu().double()
+    want = vattn_reference(sign=sign, **case)
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err < 2e-5 * max(scale, 1.0), (err, scale)
+
+
+def tail_reference(lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
+    lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo = (t.double().cpu() for t in (lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo))
+    H = w0_t.shape[-1]
+    pre = lat @ wc_t + bc
+    net = pre[:, :H]
+    for i in range(w0_t.shape[0]):
+        net = net + pre[:, (i + 1) * H:(i + 2) * H]
+        h = F.relu(net) @ w0_t[i] + b0[i]
+        net = net + F.relu(h) @ w1_t[i] + b1[i]
+    return F.relu(net) @ wo_t + bo
+
+
+@pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (128, 200, 5, 3), (1, 200, 5, 3), (515, 256, 2, 1), (77, 64, 0, 4)])
+def test_resnet_tail_forward(R, C, nb, O):
+    g = torch.Generator().manual_seed(R + C)
+    r = lambda *s: torch.randn(*s, generator=g)
+    H = 128
+    args = [r(R, C), r(C, (1 + nb) * H) / np.sqrt(C), r((1 + nb) * H) * 0.1, r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1,
+            r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1, r(H, O) / np.sqrt(H), r(O) * 0.1]
+    if nb == 0:
+        pytest.skip("n_blocks=0 packs empty tensors; covered by the validation test")
+    got = ops.resnet_tail(*[a.to(DEV).contiguous() for a in args]).cpu().double()
+    want = tail_reference(*args)
+    assert (got - want).abs().max().item() < 1e-4 * max(1.0, want.abs().max().item())
