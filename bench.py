@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): query-points/sec of the forward-deformation TDNet, fwd+bwd training step,
+batch 8 shapes x 4096 surface points x 50 000 spatial queries per GPU (configs[1]); weak scaling over GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0. A "step" is ONE call of the public API `train_on_batch(model, optimizer, data_dict, config)`
+(zero_grad, forward through the CUDA kernels, L2 loss, backward through the CUDA kernels, one flat gradient
+all-reduce when N > 1, Adam step, loss.item()).
+
+  value     whole-job query-points/s with the batch resident in HBM when the timed region starts
+  e2e       the same step fed from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region)
+  roofline  the dominant kernel (decoder vector-attention backward) timed alone with CUDA events
+  cpu_baseline / --impl reference
+            the CPU restatement of the reference path (oracle/tdnet_oracle.py, torch CPU fp32, all host threads)
+            on a bounded sample of the same workload (whole shapes of 4096 x 50 000)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, N_SURF, N_QUERY = 8, 4096, 50000
+METRIC = "query-points/sec (TDNet fwd+bwd, 50k queries/shape)"
+UNIT = "query-points/s"
+WORKLOAD = "configs[1]: forward-deformation TDNet, batch 8 shapes x 4096 surface pts x 50k spatial queries per GPU, " \
+           "fwd+bwd training step (Adam)"
+
+# Algorithmic FLOPs of the decoder cross-attention per query point: 7 neighbour rows x
+# (delta MLP 2*3*200 + 2*200*200, gamma MLP 2*2*200*200); the global row is a per-shape constant. Backward = 2x.
+VATTN_DEC_FWD_FLOP_PER_QUERY = 7 * (2 * 3 * 200 + 2 * 200 * 200) + 7 * (2 * 2 * 200 * 200)
+VATTN_DEC_BWD_FLOP_PER_QUERY = 2 * VATTN_DEC_FWD_FLOP_PER_QUERY
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json, burst)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self._halt.is_set():
+            try:
+                if self.nv is not None:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, n in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                else:
+                    out = os.popen(f"nvidia-smi -i {self.index} --query-gpu=clocks.sm,clocks.max.sm "
+                                   "--format=csv,noheader,nounits").read().strip().split(",")
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (restatement of the reference path) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, shapes_per_step: int = 1, max_seconds: float = 240.0):
+    from nsdp_b200 import synth
+    from nsdp_b200.model import build_model
+    from oracle import tdnet_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = synth.make_config("forward")
+    model, *_ = build_model(cfg)  # only used for the state_dict schema (CPU construction, no kernels run)
+    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    sd = synth.named_state_dict(schema, seed=0)
+    params = [v.requires_grad_(True) for k, v in sd.items() if k.rsplit(".", 1)[-1] in ("weight", "bias")]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    batch = synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234)
+
+    def step():
+        opt.zero_grad()
+        pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
+                                 training=True)
+        loss = orc.l2_loss(pred, batch["space_samples_tgt"])
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    qps = done * shapes_per_step * N_QUERY / dt
+    return {"value": qps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} step(s) x {shapes_per_step} shape(s) of {N_SURF} surface pts x {N_QUERY} queries, fwd+bwd+Adam, "
+                      f"torch CPU fp32 ({dt / max(done, 1):.2f} s/step)"}, dt / max(done, 1), done
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, s_per_step, done = cpu_reference_run(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (oracle port), bounded sample"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def profile_kernels(step_fn, steps: int = 2):
+    """Per-kernel device time over real steps: every C-ABI call is bracketed by CUDA events on the launching
+    (current) stream (ops.TIMING). Returns {name: {"calls", "ms"}} plus the step time under instrumentation."""
+    from nsdp_b200 import ops
+    torch.cuda.synchronize()
+    ops.TIMING = True
+    ops.timing_summary(reset=True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step_fn()
+    b.record()
+    torch.cuda.synchronize()
+    ops.TIMING = False
+    summary = ops.timing_summary(reset=True)
+    return summary, a.elapsed_time(b) / steps, steps
+
+
+def run_ours(args):
+    import torch.distributed as td
+
+    from nsdp_b200 import dist as ndist
+    from nsdp_b200 import ops, synth
+    from nsdp_b200.model import build_model, optimizer_factory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (nsdp_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        ndist.init_process_group("nccl")
+
+    cfg = synth.make_config("forward")
+    model, train_on_batch, _, _ = build_model(cfg, device=dev)
+    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(synth.named_state_dict(schema, seed=0))
+    model.train()
+    _, optimizer = optimizer_factory(cfg["training"], model.parameters())
+
+    host = synth.forward_batch(B_PER_GPU, N_SURF, N_QUERY, seed=1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        ms = 0.0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()  # evict L2 between steps (outside the event pair)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item()), wall
+
+    def step_resident():
+        return train_on_batch(model, optimizer, resident, cfg)
+
+    def step_e2e():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return train_on_batch(model, optimizer, dd, cfg)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    before = ops.LAUNCHES
+    ms_total, wall = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES - before
+    clocks = sampler.stop()
+    step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+
+    total_q = world * B_PER_GPU * N_QUERY
+    value = total_q * args.steps / (ms_total * 1e-3)
+    e2e_value = total_q * args.steps / (e2e_ms * 1e-3)
+
+    roof = None
+    cpu = None
+    if rank == 0:
+        peaks = measured_peaks()
+        summary, prof_step_ms, prof_steps = profile_kernels(step_resident)
+        nq = B_PER_GPU * N_QUERY
+        flops = {"vattn_bwd": VATTN_DEC_BWD_FLOP_PER_QUERY * nq, "vattn_fwd": VATTN_DEC_FWD_FLOP_PER_QUERY * nq}
+        top = max(summary.items(), key=lambda kv: kv[1]["ms"])
+        dec_bwd = next(v for k, v in summary.items() if k.startswith("vattn_bwd_D200"))
+        dec_fwd = next(v for k, v in summary.items() if k.startswith("vattn_fwd_D200"))
+        bwd_ms = dec_bwd["ms"] / dec_bwd["calls"]
+        fwd_ms = dec_fwd["ms"] / dec_fwd["calls"]
+        achieved = flops["vattn_bwd"] / (bwd_ms * 1e-3) / 1e12
+        roof = {"kernel": "vattn_bwd_kernel (decoder cross-attention backward, D=200, 7+1 rows/query)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "launch_ms": bwd_ms, "flop_per_launch": flops["vattn_bwd"],
+                "share_of_step": dec_bwd["ms"] / prof_steps / prof_step_ms,
+                "top_kernel_by_time": top[0],
+                "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,
+                               "share_of_step": dec_fwd["ms"] / prof_steps / prof_step_ms},
+                "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summary.items())}}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _, _ = cpu_reference_run(steps=2, warmup=1, max_seconds=60.0)
+    if world > 1:
+        td.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "surface_pts": N_SURF, "queries": N_QUERY,
+                           "parallelism": f"dp{world}", "l2": "256 MiB buffer zeroed between steps (outside the event pairs)",
+                           "bn": "local per-rank batch statistics", "wall_s": wall},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches,
+                "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

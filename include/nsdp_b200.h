@@ -130,14 +130,20 @@ typedef struct {
   const float *wg2t;  /* (D,D) transposed */
   const float *pc;    /* (D) */
   const float *vc;    /* (D) */
+  const float *wd2;   /* (D,D) un-transposed copies, read by the BACKWARD kernel only (NULL for forward) */
+  const float *wp;    /* (D,D) */
+  const float *wg2;   /* (D,D) */
   int B, M, N, K, D;
   int has_global;
   float sign;
 } nsdp_vattn_args;
 
-int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, void *stream);
+/* `stats` (2,B,M,D) or NULL: when given, the per-(centre, channel) softmax max and 1/sum are stored for the
+ * backward kernel. */
+int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, float *stats, void *stream);
 
-/* Backward of nsdp_vattn_fwd_f32 (recomputes the forward chain; nothing but inputs is saved).
+/* Backward of nsdp_vattn_fwd_f32. Recomputes the forward chain tile by tile from the inputs, the forward
+ * result `out` and the softmax statistics `stats`; no [pairs, D] activation is ever stored.
  * All gradient buffers ACCUMULATE and must be zero-filled (or hold a running sum) on entry; any of
  * them may be NULL to skip it (d_xyz_* are NULL at every level but the first, where the reference's
  * anchors are detached). */
@@ -159,7 +165,8 @@ typedef struct {
 } nsdp_vattn_grads;
 
 size_t nsdp_vattn_bwd_workspace_bytes(const nsdp_vattn_args *args);
-int nsdp_vattn_bwd_f32(const nsdp_vattn_args *args, const float *d_out /* (B,M,D) */,
+int nsdp_vattn_bwd_f32(const nsdp_vattn_args *args, const float *out /* (B,M,D) */,
+                       const float *stats /* (2,B,M,D) */, const float *d_out /* (B,M,D) */,
                        const nsdp_vattn_grads *grads, void *workspace, size_t workspace_bytes,
                        void *stream);
 
@@ -197,6 +204,11 @@ size_t nsdp_resnet_tail_bwd_workspace_bytes(const nsdp_tail_args *args);
 int nsdp_resnet_tail_bwd_f32(const nsdp_tail_args *args, const float *d_out /* (R,O) */,
                              const nsdp_tail_grads *grads, void *workspace, size_t workspace_bytes,
                              void *stream);
+
+/* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
+ * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
+ * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out. */
+int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int *err, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,90 @@
+// Hardware self-test of the tcgen05 conventions in umma.cuh: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor
+// cores (optionally with the bf16x3 split), operands written by ordinary threads in the canonical no-swizzle
+// K-major layout. tests/test_gpu_umma.py compares it with torch; every tensor-core kernel in the library relies on
+// exactly these descriptor / layout / TMEM-lane conventions.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace nsdp {
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int N, int K,
+                     int split, int *err) {
+  using namespace umma;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
+  unsigned char *a_hi = smem, *a_lo = a_hi + a_bytes, *b_hi = a_lo + a_bytes, *b_lo = b_hi + b_bytes;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+
+  for (int e = tid; e < 128 * (K / 2); e += 128) {
+    const int row = e / (K / 2), k = (e % (K / 2)) * 2;
+    uint32_t hi, lo;
+    split2(A[row * K + k], A[row * K + k + 1], hi, lo);
+    *reinterpret_cast<uint32_t *>(a_hi + canon_off(128, row, k)) = hi;
+    *reinterpret_cast<uint32_t *>(a_lo + canon_off(128, row, k)) = lo;
+  }
+  for (int e = tid; e < N * (K / 2); e += 128) {
+    const int row = e / (K / 2), k = (e % (K / 2)) * 2;
+    uint32_t hi, lo;
+    split2(B[row * K + k], B[row * K + k + 1], hi, lo);
+    *reinterpret_cast<uint32_t *>(b_hi + canon_off(N, row, k)) = hi;
+    *reinterpret_cast<uint32_t *>(b_lo + canon_off(N, row, k)) = lo;
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols *= 2;
+  if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
+    const int passes = split ? 3 : 1;
+    bool acc = false;
+    for (int p = 0; p < passes; ++p) {
+      const unsigned char *pa = (p == 1) ? a_lo : a_hi;  // hi*hi, lo*hi, hi*lo
+      const unsigned char *pb = (p == 2) ? b_lo : b_hi;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ad = smem_desc(smem_u32(pa) + ks * 2 * lbo_a, lbo_a, 128);
+        const uint64_t bd = smem_desc(smem_u32(pb) + ks * 2 * lbo_b, lbo_b, 128);
+        mma_bf16(tmem_base, ad, bd, idesc, acc);
+        acc = true;
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0, err);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[row * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+}  // namespace nsdp
+
+extern "C" int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int *err, void *stream) {
+  using namespace nsdp;
+  if (!A || !B || !D || !err || N < 16 || N > 256 || N % 16 || K < 16 || K % 16) return NSDP_ERR_INVALID_ARGUMENT;
+  const size_t smem = 2 * (size_t)(128 + N) * K * 2;
+  if (smem > 220 * 1024) return NSDP_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, split, err);
+  return check_launch();
+}

@@ -4,8 +4,8 @@ TDNet whose encoder input is cat[surface_src2cano, surface_tgt, mask].
 
 The reference runs the canonicalise ENCODER twice on identical input (flow_arbitrary.py:19-20). Here it is
 encoded once and decoded for both query sets; to stay bit-compatible with the reference's BatchNorm
-bookkeeping in train() mode (every BN updates its running stats twice per step) the second
-momentum update is replayed on the buffers instead of recomputing the pass.
+bookkeeping in train() mode (every BN updates its running stats twice per step) the single
+pass runs with the equivalent momentum 2m - m^2 and bumps num_batches_tracked twice.
 """
 from __future__ import annotations
 
@@ -29,21 +29,22 @@ class FlowArbitrary(nn.Module):
     def _canonicalize_twice(self, space_samples_src, surface_samples_src):
         cano = self.model_canonicalize
         bns = _bn_layers(cano.encoder) if self.training else []
-        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
-        encoding = cano.encode(surface_samples_src)
-        # replay the second identical running-stat update: r2 = r1 + m*(batch - r1), with
-        # batch = r0 + (r1 - r0)/m recovered from the first update
+        # Two identical passes update every running stat twice: r2 = r0 + (2m - m^2)(batch - r0). One pass with
+        # the momentum temporarily set to 2m - m^2 gives the same buffers (and num_batches_tracked += 2) without
+        # touching tensors autograd has saved.
+        saved = [bn.momentum for bn in bns]
+        for bn in bns:
+            if bn.momentum is not None:
+                bn.momentum = 2.0 * bn.momentum - bn.momentum * bn.momentum
+        try:
+            encoding = cano.encode(surface_samples_src)
+        finally:
+            for bn, m in zip(bns, saved):
+                bn.momentum = m
         with torch.no_grad():
-            for bn, (m0, v0) in zip(bns, before):
-                mom = bn.momentum
-                if mom is None:  # cumulative average: second identical sample leaves the mean unchanged
+            for bn in bns:
+                if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
-                    continue
-                batch_mean = m0 + (bn.running_mean - m0) / mom
-                batch_var = v0 + (bn.running_var - v0) / mom
-                bn.running_mean += mom * (batch_mean - bn.running_mean)
-                bn.running_var += mom * (batch_var - bn.running_var)
-                bn.num_batches_tracked += 1
         space = cano.decode(space_samples_src, encoding)
         surface = cano.decode(surface_samples_src, encoding)
         return space, surface

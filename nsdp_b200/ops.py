@@ -22,6 +22,43 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
+TIMING = False     # when True every kernel call below is bracketed by CUDA events on the launching stream
+_TIMED = []        # (name, start_event, end_event)
+
+
+class _timed:
+    """Brackets one C-ABI call with CUDA events on the current stream (only when ops.TIMING is on)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING:
+            self.b.record()
+            _TIMED.append((self.name, self.a, self.b))
+        return False
+
+
+def timing_summary(reset: bool = True) -> dict:
+    """{kernel name: {"calls": n, "ms": total}} of the calls recorded since the last reset (synchronises)."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in _TIMED:
+        e = out.setdefault(name, {"calls": 0, "ms": 0.0})
+        e["calls"] += 1
+        e["ms"] += a.elapsed_time(b)
+    if reset:
+        _TIMED.clear()
+    return out
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -58,7 +95,7 @@ def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor
     _chk_f32("points", points)
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
-    with torch.cuda.device(points.device):
+    with torch.cuda.device(points.device), _timed(f"fps_N{N}_m{nsamples}"):
         check(_lib.lib().nsdp_fps_f32(points.data_ptr(), B, N, int(nsamples), out.data_ptr(), _stream()), "nsdp_fps_f32")
     _count()
     return out
@@ -185,13 +222,15 @@ def knn(query: torch.Tensor, ref: torch.Tensor, k: int, return_d2: bool = False)
     with torch.cuda.device(query.device):
         ws_bytes = L.nsdp_knn_workspace_bytes(B, M, N, int(k))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=query.device) if ws_bytes else None
-        check(L.nsdp_knn_f32(query.data_ptr(), ref.data_ptr(), B, M, N, int(k), out.data_ptr(), _p(d2), _p(ws), ws_bytes,
-                             _stream()), "nsdp_knn_f32")
+        with _timed(f"knn_M{M}_N{N}_k{k}"):
+            check(L.nsdp_knn_f32(query.data_ptr(), ref.data_ptr(), B, M, N, int(k), out.data_ptr(), _p(d2), _p(ws),
+                                 ws_bytes, _stream()), "nsdp_knn_f32")
     _count(2 if ws_bytes else 1)
     return (out, d2) if return_d2 else out
 
 
-def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign) -> VattnArgs:
+def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, wd2=None, wp=None,
+                wg2=None) -> VattnArgs:
     B, M, _ = xyz_c.shape
     N = xyz_n.shape[1]
     D = wd2t.shape[0]
@@ -200,6 +239,7 @@ def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t
     a.xyz_c, a.xyz_n, a.idx = _p(xyz_c), _p(xyz_n), _p(idx)
     a.qp, a.kp, a.vp, a.gq, a.gv = _p(qp), _p(kp), _p(vp), _p(gq), _p(gv)
     a.wd0, a.bd0, a.wd2t, a.wpt, a.wg2t, a.pc, a.vc = _p(wd0), _p(bd0), _p(wd2t), _p(wpt), _p(wg2t), _p(pc), _p(vc)
+    a.wd2, a.wp, a.wg2 = _p(wd2), _p(wp), _p(wg2)
     a.B, a.M, a.N, a.K, a.D = B, M, N, K, D
     a.has_global = 1 if gq is not None else 0
     a.sign = float(sign)
@@ -207,7 +247,8 @@ def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t
 
 
 class _VectorAttention(torch.autograd.Function):
-    """out = nsdp_vattn_fwd_f32(...); backward = nsdp_vattn_bwd_f32 (recompute, nothing but inputs saved)."""
+    """out = nsdp_vattn_fwd_f32(...); backward = nsdp_vattn_bwd_f32, which recomputes the chain on chip from the
+    inputs + the (B,M,D) result and softmax statistics — no [pairs, D] activation is saved."""
 
     @staticmethod
     def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign):
@@ -220,18 +261,23 @@ class _VectorAttention(torch.autograd.Function):
             _chk_i32("idx", idx)
         a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign)
         out = torch.empty((a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device)
-        with torch.cuda.device(xyz_c.device):
-            check(_lib.lib().nsdp_vattn_fwd_f32(C.byref(a), out.data_ptr(), _stream()), "nsdp_vattn_fwd_f32")
+        need_bwd = any(ctx.needs_input_grad)
+        stats = torch.empty((2, a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device) if need_bwd else None
+        with torch.cuda.device(xyz_c.device), _timed(f"vattn_fwd_D{a.D}_K{a.K}_M{a.M}"):
+            check(_lib.lib().nsdp_vattn_fwd_f32(C.byref(a), out.data_ptr(), _p(stats), _stream()), "nsdp_vattn_fwd_f32")
         _count()
         ctx.sign = sign
-        ctx.save_for_backward(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc)
+        if need_bwd:
+            ctx.save_for_backward(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc = ctx.saved_tensors
+        xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats = ctx.saved_tensors
         d_out = d_out.contiguous()
-        a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, ctx.sign)
+        # the data-gradient GEMMs need the un-transposed matrices as K-major operands
+        wd2, wp, wg2 = wd2t.t().contiguous(), wpt.t().contiguous(), wg2t.t().contiguous()
+        a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, ctx.sign, wd2, wp, wg2)
         need = ctx.needs_input_grad
 
         def z(t, flag):
@@ -246,12 +292,9 @@ class _VectorAttention(torch.autograd.Function):
         gs = VattnGrads()
         for n, t in g.items():
             setattr(gs, n, _p(t))
-        L = _lib.lib()
-        with torch.cuda.device(d_out.device):
-            ws_bytes = L.nsdp_vattn_bwd_workspace_bytes(C.byref(a))
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
-            check(L.nsdp_vattn_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
-                  "nsdp_vattn_bwd_f32")
+        with torch.cuda.device(d_out.device), _timed(f"vattn_bwd_D{a.D}_K{a.K}_M{a.M}"):
+            check(_lib.lib().nsdp_vattn_bwd_f32(C.byref(a), out.data_ptr(), stats.data_ptr(), d_out.data_ptr(), C.byref(gs),
+                                                None, 0, _stream()), "nsdp_vattn_bwd_f32")
         _count()
         return (g["d_xyz_c"], g["d_xyz_n"], None, g["d_qp"], g["d_kp"], g["d_vp"], g["d_gq"], g["d_gv"], g["d_wd0"],
                 g["d_bd0"], g["d_wd2t"], g["d_wpt"], g["d_wg2t"], g["d_pc"], g["d_vc"], None)
@@ -281,7 +324,7 @@ class _ResnetTail(torch.autograd.Function):
             _chk_f32(n, t)
         a = _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
         out = torch.empty((a.R, a.O), dtype=torch.float32, device=lat2d.device)
-        with torch.cuda.device(lat2d.device):
+        with torch.cuda.device(lat2d.device), _timed("resnet_tail_fwd"):
             check(_lib.lib().nsdp_resnet_tail_fwd_f32(C.byref(a), out.data_ptr(), _stream()), "nsdp_resnet_tail_fwd_f32")
         _count()
         ctx.save_for_backward(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
@@ -300,8 +343,9 @@ class _ResnetTail(torch.autograd.Function):
         with torch.cuda.device(d_out.device):
             ws_bytes = L.nsdp_resnet_tail_bwd_workspace_bytes(C.byref(a))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
-            check(L.nsdp_resnet_tail_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
-                  "nsdp_resnet_tail_bwd_f32")
+            with _timed("resnet_tail_bwd"):
+                check(L.nsdp_resnet_tail_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
+                      "nsdp_resnet_tail_bwd_f32")
         _count()
         return tuple(grads)
 

@@ -13,7 +13,7 @@ DEV = "cuda:0"
 
 def vattn_reference(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, gq=None, gv=None):
     """float64 restatement of nsdp_vattn_fwd_f32."""
-    f = lambda t: None if t is None else t.double().cpu()
+    f = lambda t: None if t is None else (t if t.dtype == torch.float64 else t.double().cpu())
     xyz_c, xyz_n, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, gq, gv = map(
         f, (xyz_c, xyz_n, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, gq, gv))
     B, M, _ = xyz_c.shape
@@ -86,7 +86,8 @@ def test_vattn_forward(cfg, sign):
 
 
 def tail_reference(lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
-    lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo = (t.double().cpu() for t in (lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo))
+    lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo = ((t if t.dtype == torch.float64 else t.double().cpu())
+                                                   for t in (lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo))
     H = w0_t.shape[-1]
     pre = lat @ wc_t + bc
     net = pre[:, :H]
@@ -109,3 +110,75 @@ def test_resnet_tail_forward(R, C, nb, O):
     got = ops.resnet_tail(*[a.to(DEV).contiguous() for a in args]).cpu().double()
     want = tail_reference(*args)
     assert (got - want).abs().max().item() < 1e-4 * max(1.0, want.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward: GPU autograd through the CUDA kernels vs float64 CPU autograd through the restatements
+# ---------------------------------------------------------------------------------------------------------
+def _rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+BWD_CASES = [
+    dict(B=2, M=150, N=150, K=10, D=120),
+    dict(B=2, M=40, N=300, K=16, D=120),
+    dict(B=1, M=100, N=100, K=16, D=256),
+    dict(B=2, M=100, N=100, K=100, D=256, group_all=True),
+    dict(B=2, M=333, N=100, K=7, D=200, has_global=True),
+    dict(B=1, M=77, N=77, K=10, D=120, pos_only=True),
+    dict(B=1, M=9, N=13, K=3, D=64),
+]
+
+
+@pytest.mark.parametrize("cfg", BWD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_vattn_backward(cfg, sign):
+    case = _rel_case = _rand_case(seed=11, **cfg)
+    names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
+    cpu = {k: (v.double().clone().requires_grad_(True) if k in names else v) for k, v in case.items()}
+    dev = {k: (v.to(DEV).contiguous().requires_grad_(True) if k in names else (v.to(DEV) if torch.is_tensor(v) else v))
+           for k, v in case.items()}
+    want = vattn_reference(sign=sign, **cpu)
+    got = ops.vector_attention(sign=sign, **dev)
+    go = torch.randn(want.shape, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    want.backward(go)
+    got.backward(go.float().to(DEV))
+    for k in names:
+        assert dev[k].grad is not None, k
+        err = _rel_err(dev[k].grad, cpu[k].grad)
+        assert err < 2e-4, (k, err)
+
+
+def test_vattn_backward_self_attention_shares_xyz():
+    """Self attention passes the SAME tensor as centre and neighbour cloud: both gradient paths must add up."""
+    case = _rand_case(B=1, M=60, N=60, K=8, D=64, seed=3)
+    xyz64 = case["xyz_n"].double().clone().requires_grad_(True)
+    cpu = dict(case, xyz_c=xyz64, xyz_n=xyz64)
+    want = vattn_reference(sign=1.0, **cpu)
+    xyz = case["xyz_n"].to(DEV).requires_grad_(True)
+    dev = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in case.items()}
+    dev.update(xyz_c=xyz, xyz_n=xyz)
+    got = ops.vector_attention(sign=1.0, **dev)
+    want.sum().backward()
+    got.sum().backward()
+    assert _rel_err(xyz.grad, xyz64.grad) < 2e-4
+
+
+@pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (64, 200, 5, 3), (1, 200, 5, 3), (333, 256, 2, 1), (130, 64, 1, 4)])
+def test_resnet_tail_backward(R, C, nb, O):
+    g = torch.Generator().manual_seed(R + C)
+    r = lambda *s: torch.randn(*s, generator=g)
+    H = 128
+    args = [r(R, C), r(C, (1 + nb) * H) / np.sqrt(C), r((1 + nb) * H) * 0.1, r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1,
+            r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1, r(H, O) / np.sqrt(H), r(O) * 0.1]
+    cpu = [a.double().clone().requires_grad_(True) for a in args]
+    dev = [a.to(DEV).contiguous().requires_grad_(True) for a in args]
+    want = tail_reference(*cpu)
+    got = ops.resnet_tail(*dev)
+    go = torch.randn(want.shape, generator=g, dtype=torch.float64)
+    want.backward(go)
+    got.backward(go.float().to(DEV))
+    for i, (d, c) in enumerate(zip(dev, cpu)):
+        err = _rel_err(d.grad, c.grad)
+        assert err < 2e-4, (i, err)
