@@ -23,7 +23,7 @@ def _run(N, K, split, seed=0):
     return A, B, D.cpu()
 
 
-@pytest.mark.parametrize("N,K", [(16, 16), (128, 64), (208, 208), (256, 128), (64, 256)])
+@pytest.mark.parametrize("N,K", [(16, 16), (128, 64), (208, 128), (256, 128), (64, 256)])
 def test_umma_bf16(N, K):
     A, B, D = _run(N, K, 0)
     want = A.bfloat16().double() @ B.bfloat16().double().t()
