@@ -136,11 +136,15 @@ typedef struct {
   int B, M, N, K, D;
   int has_global;
   float sign;
+  int impl;           /* 0 = auto (tensor-core kernel when the shape is instantiated, else CUDA cores),
+                         1 = force the fp32 CUDA-core kernel, 2 = require the tcgen05 kernel */
 } nsdp_vattn_args;
 
 /* `stats` (2,B,M,D) or NULL: when given, the per-(centre, channel) softmax max and 1/sum are stored for the
  * backward kernel. */
-int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, float *stats, void *stream);
+size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args); /* packed bf16 hi/lo weight image (tcgen05 path) */
+int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, float *stats, void *workspace,
+                       size_t workspace_bytes, void *stream);
 
 /* Backward of nsdp_vattn_fwd_f32. Recomputes the forward chain tile by tile from the inputs, the forward
  * result `out` and the softmax statistics `stats`; no [pairs, D] activation is ever stored.

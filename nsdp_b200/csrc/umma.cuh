@@ -48,7 +48,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err = nullptr) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    ++spins;
+    // once any wait in the grid has timed out, every other wait gives up quickly too
+    if (spins > 4096u && (spins > (1u << 26) || (err && *reinterpret_cast<volatile int *>(err) != 0))) {
       if (err) atomicExch(err, 1);
       break;
     }

@@ -194,12 +194,24 @@ int vattn_validate(const nsdp_vattn_args *a) {
 
 }  // namespace nsdp
 
-extern "C" int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out, float *stats, void *stream) {
+namespace nsdp {
+int vattn_fwd_tc_dispatch(const nsdp_vattn_args *args, float *out, float *stats, void *workspace, size_t ws_bytes,
+                          cudaStream_t st, bool *handled);
+}
+
+extern "C" int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out, float *stats, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
   using namespace nsdp;
   int rc = vattn_validate(args);
   if (rc != NSDP_OK) return rc;
   if (!out) return NSDP_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
+  if (args->impl != 1) {
+    bool handled = false;
+    rc = vattn_fwd_tc_dispatch(args, out, stats, workspace, workspace_bytes, st, &handled);
+    if (handled) return rc;
+    if (args->impl == 2) return NSDP_ERR_UNSUPPORTED;
+  }
   const int krows = args->K + (args->has_global ? 1 : 0);
   const int D = args->D;
   if (D <= 120 && krows <= VCfg120::R) return launch_vattn_fwd<VCfg120>(*args, out, stats, st);

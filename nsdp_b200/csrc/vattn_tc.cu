@@ -1,0 +1,480 @@
+// Fused vector attention forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same math and same C-ABI arguments as the CUDA-core kernel in vattn.cu (see nsdp_vattn_args); this is the
+// fast path for the shapes that dominate the model (decoder cross-attention: D = 200, 7 neighbours + global
+// token; encoder blocks with 16 neighbours).
+//
+// A persistent CTA (one per SM) walks over tiles of 128 pair rows = 128/KR centres x KR rows. Per tile, with
+// every [128 x D] activation living only in shared memory / TMEM:
+//
+//   workers   H = relu(Wd0*rel + b)  (K = 3, CUDA cores)  -> bf16 hi/lo A operand in smem
+//   tensor    [gp | dl] = H * [W' ; Wd2]^T                 -> TMEM acc0, acc1   (GEMM1, N = 2*DP)
+//   workers   G = relu(gp + P)                             -> A operand (overwrites H)
+//   tensor    a = G * Wg2^T                                -> TMEM acc0         (GEMM2)
+//   workers   w = softmax over the KR rows of a centre, out = sum w * (V + dl)  -> global
+//
+// Warp roles: warp 0 streams pre-packed weight slabs from L2 with 1-D bulk async copies into a 4-stage
+// mbarrier ring; warp 1 (one elected lane) issues tcgen05.mma and commits completions to mbarriers; warps 2..9
+// are the workers (each owns one TMEM lane = one pair row, two warps per lane quarter split the columns).
+//
+// Precision: fp32 operands are split into bf16 hi + lo and every product is hi*hi + lo*hi + hi*lo accumulated in
+// fp32 (umma.cuh); the result matches the fp32 CUDA-core kernel to ~1e-6 relative.
+#include <math.h>
+
+#include "umma.cuh"
+#include "vattn_common.cuh"
+
+namespace nsdp {
+namespace vtc {
+
+using namespace umma;
+
+template <int DP_, int KR_>
+struct TcCfg {
+  static constexpr int DP = DP_;                 // padded channel count: K and N of every GEMM
+  static constexpr int KR = KR_;                 // rows per centre inside a tile (power of two, 8..32)
+  static constexpr int KSTEPS = DP / 16;
+  static constexpr int SLAB = DP * 16 * 2;       // one [DP x 16] bf16 K-major weight slab
+  static constexpr int STAGE_BYTES = 4 * SLAB;   // GEMM1 stage: W' hi, W' lo, Wd2 hi, Wd2 lo (GEMM2 uses half)
+  static constexpr int STAGES = DP > 208 ? 2 : 4;
+  static constexpr int A_HALF = 128 * DP * 2;    // bytes of the hi (or lo) A operand
+  static constexpr int WORKER_WARPS = 8;
+  static constexpr int THREADS = (2 + WORKER_WARPS) * 32;
+  static constexpr int CPT = DP / 2;             // columns per worker thread
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t ACC1_COL = 256;
+  static constexpr int CENTRES = 128 / KR;
+  // dynamic shared memory carve-up (bytes)
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_STAGE = OFF_A + 2 * A_HALF;
+  static constexpr int OFF_WD0 = OFF_STAGE + STAGES * STAGE_BYTES;   // float4[DP]
+  static constexpr int OFF_PC = OFF_WD0 + DP * 16;                   // float[DP]
+  static constexpr int OFF_VC = OFF_PC + DP * 4;                     // float[DP]
+  static constexpr int OFF_BAR = OFF_VC + DP * 4;                    // mbarriers
+  static constexpr int SMEM = OFF_BAR + 256;
+  static_assert(DP % 16 == 0 && DP <= 256 && CPT % 8 == 0, "unsupported padded width");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// Packed weight image (global memory), produced by pack_weights_kernel:
+//   GEMM1 region: for ks in [0, KSTEPS): [W' hi slab][W' lo slab][Wd2 hi slab][Wd2 lo slab]
+//   GEMM2 region: for ks in [0, KSTEPS): [Wg2 hi slab][Wg2 lo slab]
+// slab(ks) = B[:, 16ks : 16ks+16] of the (N = DP) x (K = DP) operand B[n][k] = Wt[k][n], canonical no-swizzle layout.
+template <class C>
+constexpr size_t packed_bytes() {
+  return (size_t)C::KSTEPS * 6 * C::SLAB;
+}
+
+template <class C>
+__global__ void pack_weights_kernel(const float *__restrict__ wpt, const float *__restrict__ wd2t,
+                                    const float *__restrict__ wg2t, int D, unsigned char *__restrict__ out) {
+  // one thread per (matrix m, n, k-pair)
+  const int total = 3 * C::DP * (C::DP / 2);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int m = e / (C::DP * (C::DP / 2));
+    const int rem = e - m * (C::DP * (C::DP / 2));
+    const int n = rem / (C::DP / 2), k = (rem - n * (C::DP / 2)) * 2;
+    const float *src = m == 0 ? wpt : (m == 1 ? wd2t : wg2t);
+    float x0 = 0.f, x1 = 0.f;
+    if (n < D && k < D) x0 = src[(size_t)k * D + n];
+    if (n < D && k + 1 < D) x1 = src[(size_t)(k + 1) * D + n];
+    uint32_t hi, lo;
+    split2(x0, x1, hi, lo);
+    const int ks = k >> 4, kin = k & 15;
+    const uint32_t in_slab = canon_off(C::DP, n, kin);
+    size_t base;
+    if (m < 2)
+      base = (size_t)ks * 4 * C::SLAB + (size_t)m * 2 * C::SLAB;
+    else
+      base = (size_t)C::KSTEPS * 4 * C::SLAB + (size_t)ks * 2 * C::SLAB;
+    *reinterpret_cast<uint32_t *>(out + base + in_slab) = hi;
+    *reinterpret_cast<uint32_t *>(out + base + C::SLAB + in_slab) = lo;
+  }
+}
+
+struct RowInfo {
+  int c;       // flattened centre, -1 = inactive
+  int n;       // flattened source row, or -(b+1) for the global row
+  float rx, ry, rz, flag;
+};
+
+template <class C>
+__device__ __forceinline__ RowInfo row_info(const nsdp_vattn_args &a, long long tile, int r, int krows) {
+  RowInfo ri;
+  ri.c = -1; ri.n = 0; ri.rx = ri.ry = ri.rz = 0.f; ri.flag = 0.f;
+  const int p = r / C::KR, t = r - p * C::KR;
+  const long long ci = tile * C::CENTRES + p;
+  if (ci < (long long)a.B * a.M && t < krows) {
+    const int b = (int)(ci / a.M);
+    ri.c = (int)ci;
+    if (t < a.K) {
+      const int j = a.idx ? a.idx[ci * a.K + t] : t;
+      ri.n = b * a.N + j;
+      const float *xc = a.xyz_c + ci * 3;
+      const float *xn = a.xyz_n + (size_t)ri.n * 3;
+      ri.rx = a.sign * (xc[0] - xn[0]);
+      ri.ry = a.sign * (xc[1] - xn[1]);
+      ri.rz = a.sign * (xc[2] - xn[2]);
+      ri.flag = 1.f;
+    } else {
+      ri.n = -(b + 1);
+    }
+  }
+  return ri;
+}
+
+// sum of v[0..8) over the G lanes of a group; afterwards lane j (j = lane % G < 8) holds the total of v[j] in v[0].
+template <int G>
+__device__ __forceinline__ float group_transpose_sum(float (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int off = G / 2; off >= 8; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(full, v[i], off);
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(full, send, 1);
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ int float_order_key(float x) {
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float float_from_key(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed, float *__restrict__ out,
+                    float *__restrict__ stats, long long tiles, int *err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + C::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  unsigned char *stage0 = smem + C::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + C::OFF_WD0);
+  float *pcs = reinterpret_cast<float *>(smem + C::OFF_PC);
+  float *vcs = reinterpret_cast<float *>(smem + C::OFF_VC);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+  uint64_t *full = bars;                    // [STAGES]
+  uint64_t *empty = bars + C::STAGES;       // [STAGES]
+  uint64_t *a_ready = bars + 2 * C::STAGES; // workers -> MMA (count = worker warps)
+  uint64_t *acc_done = a_ready + 1;         // MMA -> workers (tcgen05.commit)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const int krows = a.K + (a.has_global ? 1 : 0);
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = 0.f, v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      p = a.pc[kk];
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    pcs[kk] = p;
+    vcs[kk] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_ready, C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t bytes = g == 0 ? C::STAGE_BYTES : C::STAGE_BYTES / 2;
+          const unsigned char *src = packed + (g == 0 ? 0 : (size_t)C::KSTEPS * C::STAGE_BYTES);
+          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1, err);  // first round passes immediately (fresh barrier, parity trick)
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, src + (size_t)ks * bytes, bytes, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, C::DP);
+      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo);
+      uint32_t it = 0, ready_phase = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(a_ready, ready_phase, err);
+          ready_phase ^= 1;
+          tc_fence_after();
+          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            mbar_wait(&full[s], ph, err);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stage0 + (size_t)s * C::STAGE_BYTES);
+            const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
+            const bool acc = ks > 0;
+            // matrix 0 (W' in GEMM1, Wg2 in GEMM2) -> acc0
+            const uint64_t b0h = smem_desc(sb, lbo_b, 128), b0l = smem_desc(sb + C::SLAB, lbo_b, 128);
+            mma_bf16(tmem_base, ah, b0h, idesc, acc);
+            mma_bf16(tmem_base, al, b0h, idesc, true);
+            mma_bf16(tmem_base, ah, b0l, idesc, true);
+            if (g == 0) {  // matrix 1 (Wd2) -> acc1
+              const uint64_t b1h = smem_desc(sb + 2 * C::SLAB, lbo_b, 128), b1l = smem_desc(sb + 3 * C::SLAB, lbo_b, 128);
+              mma_bf16(tmem_base + C::ACC1_COL, ah, b1h, idesc, acc);
+              mma_bf16(tmem_base + C::ACC1_COL, al, b1h, idesc, true);
+              mma_bf16(tmem_base + C::ACC1_COL, ah, b1l, idesc, true);
+            }
+            mma_commit(&empty[s]);
+          }
+          mma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int ww = warp - 2;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+    const int half = ww >> 2;                // which half of the columns
+    const int r = quarter * 32 + lane;       // pair row inside the tile == TMEM lane
+    const int cb = half * C::CPT;            // first column of this thread
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const unsigned gmask = C::KR == 32 ? 0xffffffffu : (((1u << C::KR) - 1u) << (lane & ~(C::KR - 1)));
+    uint32_t done_phase = 0;
+    const long long BM = (long long)a.B * a.M;
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const RowInfo ri = row_info<C>(a, tile, r, krows);
+      // ---- H operand ---------------------------------------------------------------------------------
+#pragma unroll 2
+      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
+        float h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w0 = wd0s[k0 + j];
+          const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+          h[j] = ri.flag * fmaxf(pre, 0.f);
+        }
+        uint4 hi, lo;
+        split2(h[0], h[1], hi.x, lo.x);
+        split2(h[2], h[3], hi.y, lo.y);
+        split2(h[4], h[5], hi.z, lo.z);
+        split2(h[6], h[7], hi.w, lo.w);
+        const uint32_t off = canon_off(128, r, k0);
+        *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+        *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // ---- epilogue 1: G = relu(gp + P) -> A operand ------------------------------------------------------------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+      const float *qrow = (ri.c >= 0 && ri.n >= 0 && a.qp) ? a.qp + (size_t)ri.c * D : nullptr;
+      const float *krow = (ri.c >= 0 && ri.n >= 0 && a.kp) ? a.kp + (size_t)ri.n * D : nullptr;
+      const float *grow = (ri.c >= 0 && ri.n < 0) ? a.gq + (size_t)(-ri.n - 1) * D : nullptr;
+#pragma unroll 1
+      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
+        float v[8];
+        tmem_ld8(trow + k0, v);
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const int col = k0 + j;
+          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col < D) {
+            if (grow) {
+              p = ldg4(grow + col);
+            } else {
+              p = *reinterpret_cast<const float4 *>(pcs + col);
+              if (qrow) {
+                const float4 q = ldg4(qrow + col);
+                p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+              }
+              if (krow) {
+                const float4 kq = ldg4(krow + col);
+                p.x -= kq.x; p.y -= kq.y; p.z -= kq.z; p.w -= kq.w;
+              }
+            }
+          }
+          const bool on = ri.c >= 0 && col < D;
+          g[j] = on ? fmaxf(v[j] + p.x, 0.f) : 0.f;
+          g[j + 1] = on ? fmaxf(v[j + 1] + p.y, 0.f) : 0.f;
+          g[j + 2] = on ? fmaxf(v[j + 2] + p.z, 0.f) : 0.f;
+          g[j + 3] = on ? fmaxf(v[j + 3] + p.w, 0.f) : 0.f;
+        }
+        uint4 hi, lo;
+        split2(g[0], g[1], hi.x, lo.x);
+        split2(g[2], g[3], hi.y, lo.y);
+        split2(g[4], g[5], hi.z, lo.z);
+        split2(g[6], g[7], hi.w, lo.w);
+        const uint32_t off = canon_off(128, r, k0);
+        *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+        *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // ---- epilogue 2: softmax over the KR rows of a centre, out = sum w * (V + dl) ---------------------------------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+      const bool row_on = ri.c >= 0;                     // rows that take part in the softmax
+      const float *vrow = (row_on && ri.n >= 0 && a.vp) ? a.vp + (size_t)ri.n * D : nullptr;
+      const float *gvrow = (row_on && ri.n < 0) ? a.gv + (size_t)(-ri.n - 1) * D : nullptr;
+      // the centre of this lane's group (identical for the KR lanes of the group)
+      const long long ci = tile * C::CENTRES + r / C::KR;
+      const int gl = lane & (C::KR - 1);
+#pragma unroll 1
+      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
+        float av[8], dl[8];
+        tmem_ld8(trow + k0, av);
+        tmem_ld8(trow + C::ACC1_COL + k0, dl);
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const int col = k0 + j;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col < D && row_on) {
+            if (gvrow) {
+              t = ldg4(gvrow + col);
+            } else {
+              t = *reinterpret_cast<const float4 *>(vcs + col);
+              if (vrow) {
+                const float4 vv = ldg4(vrow + col);
+                t.x += vv.x; t.y += vv.y; t.z += vv.z; t.w += vv.w;
+              }
+              t.x += dl[j]; t.y += dl[j + 1]; t.z += dl[j + 2]; t.w += dl[j + 3];
+            }
+          }
+          s[j] = t.x; s[j + 1] = t.y; s[j + 2] = t.z; s[j + 3] = t.w;
+        }
+        float e[8], es[8], mxv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = row_on ? av[j] : -INFINITY;
+          const int key = __reduce_max_sync(gmask, float_order_key(x));
+          const float mx = float_from_key(key);
+          mxv[j] = mx;
+          const float ex = row_on ? __expf(x - mx) : 0.f;
+          e[j] = ex;
+          es[j] = ex * s[j];
+        }
+        const float se = group_transpose_sum<C::KR>(e, lane);
+        const float ses = group_transpose_sum<C::KR>(es, lane);
+        if (gl < 8) {
+          const int col = k0 + gl;
+          if (ci < BM && col < D) {
+            const float inv = 1.f / se;
+            out[ci * D + col] = ses * inv;
+            if (stats) {
+              // mxv[gl] without dynamic register indexing
+              float m = mxv[0];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) m = (gl == j) ? mxv[j] : m;
+              stats[ci * D + col] = m;
+              stats[(BM + ci) * D + col] = inv;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <class C>
+static int launch(const nsdp_vattn_args &a, float *out, float *stats, void *workspace, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = packed_bytes<C>() + 16;
+  if (!workspace || ws_bytes < need) return NSDP_ERR_WORKSPACE;
+  unsigned char *packed = (unsigned char *)workspace;
+  int *err = (int *)(packed + packed_bytes<C>());
+  cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  pack_weights_kernel<C><<<64, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
+  int rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  const long long tiles = ceil_div((long long)a.B * a.M, (long long)C::CENTRES);
+  auto kern = vattn_fwd_tc_kernel<C>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, out, stats, tiles, err);
+  return check_launch();
+}
+
+// Which (DP, KR) instantiation serves these arguments; 0 = not supported by the tensor-core path.
+static int pick(const nsdp_vattn_args &a) {
+  const int krows = a.K + (a.has_global ? 1 : 0);
+  if (a.D % 4 != 0) return 0;
+  if (a.D <= 208 && a.D > 128 && krows == 8) return 1;    // decoder: D = 200, 7 + global
+  return 0;
+}
+
+}  // namespace vtc
+}  // namespace nsdp
+
+extern "C" size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args) {
+  using namespace nsdp;
+  if (!args) return 0;
+  switch (vtc::pick(*args)) {
+    case 1: return vtc::packed_bytes<vtc::TcCfg<208, 8>>() + 16;
+    default: return 0;
+  }
+}
+
+namespace nsdp {
+int vattn_fwd_tc_dispatch(const nsdp_vattn_args *args, float *out, float *stats, void *workspace, size_t ws_bytes,
+                          cudaStream_t st, bool *handled) {
+  *handled = true;
+  switch (vtc::pick(*args)) {
+    case 1: return vtc::launch<vtc::TcCfg<208, 8>>(*args, out, stats, workspace, ws_bytes, st);
+    default: *handled = false; return NSDP_OK;
+  }
+}
+}  // namespace nsdp

@@ -22,6 +22,9 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
+# 0 = auto (tcgen05 kernel where instantiated), 1 = fp32 CUDA-core kernels only, 2 = require tcgen05
+VATTN_IMPL = int(__import__("os").environ.get("NSDP_B200_VATTN_IMPL", "0"))
+
 TIMING = False     # when True every kernel call below is bracketed by CUDA events on the launching stream
 _TIMED = []        # (name, start_event, end_event)
 
@@ -243,6 +246,7 @@ def _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t
     a.B, a.M, a.N, a.K, a.D = B, M, N, K, D
     a.has_global = 1 if gq is not None else 0
     a.sign = float(sign)
+    a.impl = VATTN_IMPL
     return a
 
 
@@ -263,8 +267,13 @@ class _VectorAttention(torch.autograd.Function):
         out = torch.empty((a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device)
         need_bwd = any(ctx.needs_input_grad)
         stats = torch.empty((2, a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device) if need_bwd else None
-        with torch.cuda.device(xyz_c.device), _timed(f"vattn_fwd_D{a.D}_K{a.K}_M{a.M}"):
-            check(_lib.lib().nsdp_vattn_fwd_f32(C.byref(a), out.data_ptr(), _p(stats), _stream()), "nsdp_vattn_fwd_f32")
+        L = _lib.lib()
+        with torch.cuda.device(xyz_c.device):
+            ws_bytes = L.nsdp_vattn_fwd_workspace_bytes(C.byref(a)) if a.impl != 1 else 0
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz_c.device) if ws_bytes else None
+            with _timed(f"vattn_fwd_D{a.D}_K{a.K}_M{a.M}"):
+                check(L.nsdp_vattn_fwd_f32(C.byref(a), out.data_ptr(), _p(stats), _p(ws), ws_bytes, _stream()),
+                      "nsdp_vattn_fwd_f32")
         _count()
         ctx.sign = sign
         if need_bwd:

@@ -182,3 +182,37 @@ def test_resnet_tail_backward(R, C, nb, O):
     for i, (d, c) in enumerate(zip(dev, cpu)):
         err = _rel_err(d.grad, c.grad)
         assert err < 2e-4, (i, err)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 path (bf16x3 split precision on the tensor cores) vs the fp64 restatement and vs the fp32 CUDA-core kernel
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [16, 777, 5000, 40000])
+def test_vattn_tc_decoder_forward(M, monkeypatch):
+    case = _rand_case(B=2, M=M, N=100, K=7, D=200, has_global=True, seed=M)
+    dev = {k: (v.to(DEV).contiguous() if torch.is_tensor(v) else v) for k, v in case.items()}
+    monkeypatch.setattr(ops, "VATTN_IMPL", 2)   # require the tensor-core kernel
+    got_tc = ops.vector_attention(sign=1.0, **dev).cpu().double()
+    monkeypatch.setattr(ops, "VATTN_IMPL", 1)   # fp32 CUDA cores
+    got_ff = ops.vector_attention(sign=1.0, **dev).cpu().double()
+    scale = max(got_ff.abs().max().item(), 1.0)
+    assert (got_tc - got_ff).abs().max().item() < 3e-5 * scale
+    if M <= 5000:
+        want = vattn_reference(sign=1.0, **case)
+        assert (got_tc - want).abs().max().item() < 3e-5 * scale
+
+
+def test_vattn_tc_stats_feed_backward(monkeypatch):
+    """Softmax statistics written by the tensor-core forward drive the (CUDA-core) backward kernel."""
+    case = _rand_case(B=2, M=300, N=100, K=7, D=200, has_global=True, seed=5)
+    names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
+    cpu = {k: (v.double().clone().requires_grad_(True) if k in names else v) for k, v in case.items()}
+    dev = {k: (v.to(DEV).contiguous().requires_grad_(True) if k in names else (v.to(DEV) if torch.is_tensor(v) else v))
+           for k, v in case.items()}
+    monkeypatch.setattr(ops, "VATTN_IMPL", 2)
+    want = vattn_reference(sign=1.0, **cpu)
+    got = ops.vector_attention(sign=1.0, **dev)
+    want.sum().backward()
+    got.sum().backward()
+    for k in names:
+        assert _rel_err(dev[k].grad, cpu[k].grad) < 2e-4, k
