@@ -190,9 +190,12 @@ typedef struct {
   const float *w0_t, *b0, *w1_t, *b1;
   const float *wo_t, *bo;
   int R, C, H, O, n_blocks;
+  int impl;  /* 0 = auto (tcgen05 kernel when instantiated), 1 = fp32 CUDA-core kernel, 2 = require tcgen05 */
 } nsdp_tail_args;
 
-int nsdp_resnet_tail_fwd_f32(const nsdp_tail_args *args, float *out /* (R,O) */, void *stream);
+size_t nsdp_resnet_tail_fwd_workspace_bytes(const nsdp_tail_args *args); /* packed bf16 hi/lo weights (tcgen05 path) */
+int nsdp_resnet_tail_fwd_f32(const nsdp_tail_args *args, float *out /* (R,O) */, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* Backward of nsdp_resnet_tail_fwd_f32 (recomputes the activations tile by tile). Gradient buffers have the
  * layouts of the corresponding (transposed, concatenated) forward arguments, ACCUMULATE, and must be

@@ -39,7 +39,7 @@ class TailArgs(C.Structure):
         ("lat", C.c_void_p), ("wc_t", C.c_void_p), ("bc", C.c_void_p),
         ("w0_t", C.c_void_p), ("b0", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p),
         ("wo_t", C.c_void_p), ("bo", C.c_void_p),
-        ("R", C.c_int), ("C", C.c_int), ("H", C.c_int), ("O", C.c_int), ("n_blocks", C.c_int),
+        ("R", C.c_int), ("C", C.c_int), ("H", C.c_int), ("O", C.c_int), ("n_blocks", C.c_int), ("impl", C.c_int),
     ]
 
 
@@ -71,7 +71,8 @@ SIGNATURES = {
     "nsdp_vattn_fwd_f32": (_I, [C.POINTER(VattnArgs), _P, _P, _P, _SZ, _P]),
     "nsdp_vattn_bwd_workspace_bytes": (_SZ, [C.POINTER(VattnArgs)]),
     "nsdp_vattn_bwd_f32": (_I, [C.POINTER(VattnArgs), _P, _P, _P, C.POINTER(VattnGrads), _P, _SZ, _P]),
-    "nsdp_resnet_tail_fwd_f32": (_I, [C.POINTER(TailArgs), _P, _P]),
+    "nsdp_resnet_tail_fwd_workspace_bytes": (_SZ, [C.POINTER(TailArgs)]),
+    "nsdp_resnet_tail_fwd_f32": (_I, [C.POINTER(TailArgs), _P, _P, _SZ, _P]),
     "nsdp_resnet_tail_bwd_workspace_bytes": (_SZ, [C.POINTER(TailArgs)]),
     "nsdp_resnet_tail_bwd_f32": (_I, [C.POINTER(TailArgs), _P, C.POINTER(TailGrads), _P, _SZ, _P]),
     "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),

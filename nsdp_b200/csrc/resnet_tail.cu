@@ -122,12 +122,37 @@ __global__ void __launch_bounds__(THREADS, 1) resnet_tail_fwd_kernel(const nsdp_
 }  // namespace tail
 }  // namespace nsdp
 
-extern "C" int nsdp_resnet_tail_fwd_f32(const nsdp_tail_args *a, float *out, void *stream) {
+namespace nsdp {
+size_t tail_tc_workspace_bytes(const nsdp_tail_args *a);
+int tail_tc_dispatch(const nsdp_tail_args *a, float *out, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled);
+}
+
+static int tail_validate(const nsdp_tail_args *a) {
   using namespace nsdp;
-  if (!a || !out || !a->lat || !a->wc_t || !a->bc || !a->wo_t || !a->bo) return NSDP_ERR_INVALID_ARGUMENT;
+  if (!a || !a->lat || !a->wc_t || !a->bc || !a->wo_t || !a->bo) return NSDP_ERR_INVALID_ARGUMENT;
   if (a->n_blocks > 0 && (!a->w0_t || !a->b0 || !a->w1_t || !a->b1)) return NSDP_ERR_INVALID_ARGUMENT;
   if (a->R <= 0 || a->C <= 0 || a->O <= 0 || a->n_blocks < 0) return NSDP_ERR_INVALID_ARGUMENT;
   if (a->H != tail::H || a->C % 4 != 0 || a->C > 256 || a->O > 4) return NSDP_ERR_UNSUPPORTED;
+  return NSDP_OK;
+}
+
+extern "C" size_t nsdp_resnet_tail_fwd_workspace_bytes(const nsdp_tail_args *a) {
+  if (tail_validate(a) != NSDP_OK || a->impl == 1) return 0;
+  return nsdp::tail_tc_workspace_bytes(a);
+}
+
+extern "C" int nsdp_resnet_tail_fwd_f32(const nsdp_tail_args *a, float *out, void *workspace, size_t workspace_bytes,
+                                        void *stream) {
+  using namespace nsdp;
+  int rc = tail_validate(a);
+  if (rc != NSDP_OK) return rc;
+  if (!out) return NSDP_ERR_INVALID_ARGUMENT;
+  if (a->impl != 1) {
+    bool handled = false;
+    rc = tail_tc_dispatch(a, out, workspace, workspace_bytes, (cudaStream_t)stream, &handled);
+    if (handled) return rc;
+    if (a->impl == 2) return NSDP_ERR_UNSUPPORTED;
+  }
   const size_t smem = tail::smem_bytes(a->C);
   cudaError_t e = cudaFuncSetAttribute(tail::resnet_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);

@@ -38,9 +38,11 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 4 * SLAB;   // GEMM1 stage: W' hi, W' lo, Wd2 hi, Wd2 lo (GEMM2 uses half)
   static constexpr int STAGES = DP > 208 ? 2 : 4;
   static constexpr int A_HALF = 128 * DP * 2;    // bytes of the hi (or lo) A operand
-  static constexpr int WORKER_WARPS = 8;
+  static constexpr int NPART = 4;                // worker warps per TMEM lane quarter (they split the columns)
+  static constexpr int WORKER_WARPS = 4 * NPART;
   static constexpr int THREADS = (2 + WORKER_WARPS) * 32;
-  static constexpr int CPT = DP / 2;             // columns per worker thread
+  static constexpr int CHUNKS = DP / 8;          // 8-column chunks per row
+  static constexpr int MAXCH = (CHUNKS + NPART - 1) / NPART;  // chunks per worker thread (upper bound)
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr uint32_t ACC1_COL = 256;
   static constexpr int CENTRES = 128 / KR;
@@ -52,7 +54,7 @@ struct TcCfg {
   static constexpr int OFF_VC = OFF_PC + DP * 4;                     // float[DP]
   static constexpr int OFF_BAR = OFF_VC + DP * 4;                    // mbarriers
   static constexpr int SMEM = OFF_BAR + 256;
-  static_assert(DP % 16 == 0 && DP <= 256 && CPT % 8 == 0, "unsupported padded width");
+  static_assert(DP % 16 == 0 && DP <= 256, "unsupported padded width");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -274,149 +276,170 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
     // ===================== workers =====================
     const int ww = warp - 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
-    const int half = ww >> 2;                // which half of the columns
+    const int part = ww >> 2;                // which slice of the columns
     const int r = quarter * 32 + lane;       // pair row inside the tile == TMEM lane
-    const int cb = half * C::CPT;            // first column of this thread
+    const int ch0 = part * C::CHUNKS / C::NPART, ch1 = (part + 1) * C::CHUNKS / C::NPART;
+    const int nch = ch1 - ch0;               // 8-column chunks owned by this thread (<= MAXCH)
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const unsigned gmask = C::KR == 32 ? 0xffffffffu : (((1u << C::KR) - 1u) << (lane & ~(C::KR - 1)));
     uint32_t done_phase = 0;
     const long long BM = (long long)a.B * a.M;
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const RowInfo ri = row_info<C>(a, tile, r, krows);
+      const bool row_on = ri.c >= 0;
+      const bool is_glob = row_on && ri.n < 0;
       // ---- H operand ---------------------------------------------------------------------------------
-#pragma unroll 2
-      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
-        float h[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 w0 = wd0s[k0 + j];
-          const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
-          h[j] = ri.flag * fmaxf(pre, 0.f);
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w0 = wd0s[k0 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
+          }
+          uint4 hi, lo;
+          split2(h[0], h[1], hi.x, lo.x);
+          split2(h[2], h[3], hi.y, lo.y);
+          split2(h[4], h[5], hi.z, lo.z);
+          split2(h[6], h[7], hi.w, lo.w);
+          const uint32_t off = canon_off(128, r, k0);
+          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
         }
-        uint4 hi, lo;
-        split2(h[0], h[1], hi.x, lo.x);
-        split2(h[2], h[3], hi.y, lo.y);
-        split2(h[4], h[5], hi.z, lo.z);
-        split2(h[6], h[7], hi.w, lo.w);
-        const uint32_t off = canon_off(128, r, k0);
-        *reinterpret_cast<uint4 *>(A_hi + off) = hi;
-        *reinterpret_cast<uint4 *>(A_lo + off) = lo;
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
 
+      // ---- gather P = pc + qp - kp (or gq for the global row) for this thread's columns while GEMM1 runs ---------
+      float P[C::MAXCH][8];
+      {
+        const float *qrow = (row_on && !is_glob && a.qp) ? a.qp + (size_t)ri.c * D : nullptr;
+        const float *krow = (row_on && !is_glob && a.kp) ? a.kp + (size_t)ri.n * D : nullptr;
+        const float *grow = is_glob ? a.gq + (size_t)(-ri.n - 1) * D : nullptr;
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = (ch0 + q) * 8 + j;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nch && col < D && row_on) {
+              if (grow) {
+                p = ldg4(grow + col);
+              } else {
+                p = *reinterpret_cast<const float4 *>(pcs + col);
+                if (qrow) {
+                  const float4 t = ldg4(qrow + col);
+                  p.x += t.x; p.y += t.y; p.z += t.z; p.w += t.w;
+                }
+                if (krow) {
+                  const float4 t = ldg4(krow + col);
+                  p.x -= t.x; p.y -= t.y; p.z -= t.z; p.w -= t.w;
+                }
+              }
+            }
+            P[q][j] = p.x; P[q][j + 1] = p.y; P[q][j + 2] = p.z; P[q][j + 3] = p.w;
+          }
+        }
+      }
+
       // ---- epilogue 1: G = relu(gp + P) -> A operand ------------------------------------------------------------
       mbar_wait(acc_done, done_phase, err);
       done_phase ^= 1;
       tc_fence_after();
-      const float *qrow = (ri.c >= 0 && ri.n >= 0 && a.qp) ? a.qp + (size_t)ri.c * D : nullptr;
-      const float *krow = (ri.c >= 0 && ri.n >= 0 && a.kp) ? a.kp + (size_t)ri.n * D : nullptr;
-      const float *grow = (ri.c >= 0 && ri.n < 0) ? a.gq + (size_t)(-ri.n - 1) * D : nullptr;
-#pragma unroll 1
-      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
-        float v[8];
-        tmem_ld8(trow + k0, v);
-        float g[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const int col = k0 + j;
-          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col < D) {
-            if (grow) {
-              p = ldg4(grow + col);
-            } else {
-              p = *reinterpret_cast<const float4 *>(pcs + col);
-              if (qrow) {
-                const float4 q = ldg4(qrow + col);
-                p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
-              }
-              if (krow) {
-                const float4 kq = ldg4(krow + col);
-                p.x -= kq.x; p.y -= kq.y; p.z -= kq.z; p.w -= kq.w;
-              }
-            }
-          }
-          const bool on = ri.c >= 0 && col < D;
-          g[j] = on ? fmaxf(v[j] + p.x, 0.f) : 0.f;
-          g[j + 1] = on ? fmaxf(v[j + 1] + p.y, 0.f) : 0.f;
-          g[j + 2] = on ? fmaxf(v[j + 2] + p.z, 0.f) : 0.f;
-          g[j + 3] = on ? fmaxf(v[j + 3] + p.w, 0.f) : 0.f;
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float v[8];
+          tmem_ld8(trow + k0, v);
+          float g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = (row_on && k0 + j < D) ? fmaxf(v[j] + P[q][j], 0.f) : 0.f;
+          uint4 hi, lo;
+          split2(g[0], g[1], hi.x, lo.x);
+          split2(g[2], g[3], hi.y, lo.y);
+          split2(g[4], g[5], hi.z, lo.z);
+          split2(g[6], g[7], hi.w, lo.w);
+          const uint32_t off = canon_off(128, r, k0);
+          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
         }
-        uint4 hi, lo;
-        split2(g[0], g[1], hi.x, lo.x);
-        split2(g[2], g[3], hi.y, lo.y);
-        split2(g[4], g[5], hi.z, lo.z);
-        split2(g[6], g[7], hi.w, lo.w);
-        const uint32_t off = canon_off(128, r, k0);
-        *reinterpret_cast<uint4 *>(A_hi + off) = hi;
-        *reinterpret_cast<uint4 *>(A_lo + off) = lo;
       }
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
 
+      // ---- gather V = vc + vp (or gv) while GEMM2 runs (re-uses the P registers) ----------------------------------
+      {
+        const float *vrow = (row_on && !is_glob && a.vp) ? a.vp + (size_t)ri.n * D : nullptr;
+        const float *gvrow = is_glob ? a.gv + (size_t)(-ri.n - 1) * D : nullptr;
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = (ch0 + q) * 8 + j;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nch && col < D && row_on) {
+              if (gvrow) {
+                t = ldg4(gvrow + col);
+              } else {
+                t = *reinterpret_cast<const float4 *>(vcs + col);
+                if (vrow) {
+                  const float4 u = ldg4(vrow + col);
+                  t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+              }
+            }
+            P[q][j] = t.x; P[q][j + 1] = t.y; P[q][j + 2] = t.z; P[q][j + 3] = t.w;
+          }
+        }
+      }
+
       // ---- epilogue 2: softmax over the KR rows of a centre, out = sum w * (V + dl) ---------------------------------
       mbar_wait(acc_done, done_phase, err);
       done_phase ^= 1;
       tc_fence_after();
-      const bool row_on = ri.c >= 0;                     // rows that take part in the softmax
-      const float *vrow = (row_on && ri.n >= 0 && a.vp) ? a.vp + (size_t)ri.n * D : nullptr;
-      const float *gvrow = (row_on && ri.n < 0) ? a.gv + (size_t)(-ri.n - 1) * D : nullptr;
-      // the centre of this lane's group (identical for the KR lanes of the group)
-      const long long ci = tile * C::CENTRES + r / C::KR;
+      const long long ci = tile * C::CENTRES + r / C::KR;   // centre of this lane's group
       const int gl = lane & (C::KR - 1);
-#pragma unroll 1
-      for (int k0 = cb; k0 < cb + C::CPT; k0 += 8) {
-        float av[8], dl[8];
-        tmem_ld8(trow + k0, av);
-        tmem_ld8(trow + C::ACC1_COL + k0, dl);
-        float s[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const int col = k0 + j;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col < D && row_on) {
-            if (gvrow) {
-              t = ldg4(gvrow + col);
-            } else {
-              t = *reinterpret_cast<const float4 *>(vcs + col);
-              if (vrow) {
-                const float4 vv = ldg4(vrow + col);
-                t.x += vv.x; t.y += vv.y; t.z += vv.z; t.w += vv.w;
-              }
-              t.x += dl[j]; t.y += dl[j + 1]; t.z += dl[j + 2]; t.w += dl[j + 3];
-            }
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float av[8], dl[8];
+          tmem_ld8(trow + k0, av);
+          tmem_ld8(trow + C::ACC1_COL + k0, dl);
+          float e[8], es[8], mxv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = row_on ? av[j] : -INFINITY;
+            float mx = x;
+#pragma unroll
+            for (int off = 1; off < C::KR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            mxv[j] = mx;
+            const float ex = row_on ? __expf(x - mx) : 0.f;
+            const float sv = is_glob ? P[q][j] : P[q][j] + dl[j];
+            e[j] = ex;
+            es[j] = ex * sv;
           }
-          s[j] = t.x; s[j + 1] = t.y; s[j + 2] = t.z; s[j + 3] = t.w;
-        }
-        float e[8], es[8], mxv[8];
+          const float se = group_transpose_sum<C::KR>(e, lane);
+          const float ses = group_transpose_sum<C::KR>(es, lane);
+          if (gl < 8) {
+            const int col = k0 + gl;
+            if (ci < BM && col < D) {
+              const float inv = 1.f / se;
+              out[ci * D + col] = ses * inv;
+              if (stats) {
+                float m = mxv[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = row_on ? av[j] : -INFINITY;
-          const int key = __reduce_max_sync(gmask, float_order_key(x));
-          const float mx = float_from_key(key);
-          mxv[j] = mx;
-          const float ex = row_on ? __expf(x - mx) : 0.f;
-          e[j] = ex;
-          es[j] = ex * s[j];
-        }
-        const float se = group_transpose_sum<C::KR>(e, lane);
-        const float ses = group_transpose_sum<C::KR>(es, lane);
-        if (gl < 8) {
-          const int col = k0 + gl;
-          if (ci < BM && col < D) {
-            const float inv = 1.f / se;
-            out[ci * D + col] = ses * inv;
-            if (stats) {
-              // mxv[gl] without dynamic register indexing
-              float m = mxv[0];
-#pragma unroll
-              for (int j = 1; j < 8; ++j) m = (gl == j) ? mxv[j] : m;
-              stats[ci * D + col] = m;
-              stats[(BM + ci) * D + col] = inv;
+                for (int j = 1; j < 8; ++j) m = (gl == j) ? mxv[j] : m;
+                stats[ci * D + col] = m;
+                stats[(BM + ci) * D + col] = inv;
+              }
             }
           }
         }

@@ -25,6 +25,8 @@ def _count(n: int = 1) -> None:
 # 0 = auto (tcgen05 kernel where instantiated), 1 = fp32 CUDA-core kernels only, 2 = require tcgen05
 VATTN_IMPL = int(__import__("os").environ.get("NSDP_B200_VATTN_IMPL", "0"))
 
+TAIL_IMPL = int(__import__("os").environ.get("NSDP_B200_TAIL_IMPL", "0"))
+
 TIMING = False     # when True every kernel call below is bracketed by CUDA events on the launching stream
 _TIMED = []        # (name, start_event, end_event)
 
@@ -323,6 +325,7 @@ def _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo) -> TailArgs:
     a.H = w0_t.shape[-1]
     a.O = wo_t.shape[1]
     a.n_blocks = w0_t.shape[0]
+    a.impl = TAIL_IMPL
     return a
 
 
@@ -333,8 +336,13 @@ class _ResnetTail(torch.autograd.Function):
             _chk_f32(n, t)
         a = _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
         out = torch.empty((a.R, a.O), dtype=torch.float32, device=lat2d.device)
-        with torch.cuda.device(lat2d.device), _timed("resnet_tail_fwd"):
-            check(_lib.lib().nsdp_resnet_tail_fwd_f32(C.byref(a), out.data_ptr(), _stream()), "nsdp_resnet_tail_fwd_f32")
+        L = _lib.lib()
+        with torch.cuda.device(lat2d.device):
+            ws_bytes = L.nsdp_resnet_tail_fwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=lat2d.device) if ws_bytes else None
+            with _timed("resnet_tail_fwd"):
+                check(L.nsdp_resnet_tail_fwd_f32(C.byref(a), out.data_ptr(), _p(ws), ws_bytes, _stream()),
+                      "nsdp_resnet_tail_fwd_f32")
         _count()
         ctx.save_for_backward(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
         return out

@@ -216,3 +216,23 @@ def test_vattn_tc_stats_feed_backward(monkeypatch):
     got.sum().backward()
     for k in names:
         assert _rel_err(dev[k].grad, cpu[k].grad) < 2e-4, k
+
+
+@pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (128, 200, 5, 3), (1, 200, 5, 3), (40000, 200, 5, 3), (515, 128, 2, 1),
+                                      (300, 64, 1, 4)])
+def test_resnet_tail_tc_forward(R, C, nb, O, monkeypatch):
+    g = torch.Generator().manual_seed(R + C)
+    r = lambda *s: torch.randn(*s, generator=g)
+    H = 128
+    args = [r(R, C), r(C, (1 + nb) * H) / np.sqrt(C), r((1 + nb) * H) * 0.1, r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1,
+            r(nb, H, H) / np.sqrt(H), r(nb, H) * 0.1, r(H, O) / np.sqrt(H), r(O) * 0.1]
+    dev = [a.to(DEV).contiguous() for a in args]
+    monkeypatch.setattr(ops, "TAIL_IMPL", 2)
+    got = ops.resnet_tail(*dev).cpu().double()
+    monkeypatch.setattr(ops, "TAIL_IMPL", 1)
+    ff = ops.resnet_tail(*dev).cpu().double()
+    scale = max(1.0, ff.abs().max().item())
+    assert (got - ff).abs().max().item() < 5e-5 * scale
+    if R <= 1000:
+        want = tail_reference(*args)
+        assert (got - want).abs().max().item() < 5e-5 * scale
