@@ -1,0 +1,53 @@
+"""Run an UNCHANGED reference script (train.py / test.py / run.py) on top of nsdp_b200:
+
+    python -m nsdp_b200.launch /path/to/NSDP/train.py config.yaml [script args...]
+    python -m torch.distributed.run --nproc-per-node 8 -m nsdp_b200.launch /path/to/NSDP/train.py config.yaml ...
+
+The scripts do `from model import build_model, optimizer_factory`, `import model.learningrate` and (through the
+model files) `import pointnet2_ops_lib.pointnet2_ops.pointnet2_utils` (train.py:12-13, model/encoder/blocks.py:15).
+Those names are pre-bound in sys.modules to the nsdp_b200 mirrors, so the script's own `model/` directory is never
+imported. Under torchrun every rank pins itself to its GPU via CUDA_VISIBLE_DEVICES so that the script's hard-wired
+`cuda:0` (train.py:74-77) is the rank's device; build_model() then joins the process group and the train_on_batch_*
+functions all-reduce gradients (nsdp_b200/dist.py).
+"""
+from __future__ import annotations
+
+import os
+import runpy
+import sys
+import types
+
+
+def install_aliases() -> None:
+    import nsdp_b200.model as model
+    import nsdp_b200.pointnet2_ops as p2
+    sys.modules["model"] = model
+    for sub in ("deformation_networks", "flow_arbitrary", "learningrate", "utils", "encoder", "decoder"):
+        sys.modules[f"model.{sub}"] = __import__(f"nsdp_b200.model.{sub}", fromlist=["_"])
+    sys.modules["pointnet2_ops"] = p2
+    sys.modules["pointnet2_ops._ext"] = p2._ext
+    sys.modules["pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
+    lib = types.ModuleType("pointnet2_ops_lib")
+    lib.pointnet2_ops = p2
+    lib.__path__ = []
+    sys.modules["pointnet2_ops_lib"] = lib
+    sys.modules["pointnet2_ops_lib.pointnet2_ops"] = p2
+    sys.modules["pointnet2_ops_lib.pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit("usage: python -m nsdp_b200.launch <script.py> [args...]")
+    local_rank = os.environ.get("LOCAL_RANK")
+    if local_rank is not None and "NSDP_B200_KEEP_VISIBLE" not in os.environ:
+        os.environ["CUDA_VISIBLE_DEVICES"] = local_rank
+    install_aliases()
+    script = argv[0]
+    sys.argv = argv
+    sys.path.insert(0, os.path.dirname(os.path.abspath(script)))
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
