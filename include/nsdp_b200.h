@@ -214,8 +214,11 @@ int nsdp_resnet_tail_bwd_f32(const nsdp_tail_args *args, const float *d_out /* (
 
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
- * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out. */
-int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int *err, void *stream);
+ * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.
+ * mn == 0: operands K-major as stated. mn != 0: A is given as X (K,128), B as Y (K,N) and D = X^T * Y, the tiles
+ * being consumed as MN-major operands (the weight-gradient kernels' use of activation tiles). */
+int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int mn, int *err,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -75,7 +75,7 @@ SIGNATURES = {
     "nsdp_resnet_tail_fwd_f32": (_I, [C.POINTER(TailArgs), _P, _P, _SZ, _P]),
     "nsdp_resnet_tail_bwd_workspace_bytes": (_SZ, [C.POINTER(TailArgs)]),
     "nsdp_resnet_tail_bwd_f32": (_I, [C.POINTER(TailArgs), _P, C.POINTER(TailGrads), _P, _SZ, _P]),
-    "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,157 @@
+// Weight-gradient products on tcgen05:  out[m][n] += sum_r X[r][m] * Y[r][n]   ("TN" GEMM, reduction over pair rows).
+//
+// The backward chain kernels (vattn_bwd_tc.cu, resnet_tail_bwd_tc.cu) cannot keep the d x d weight-gradient
+// accumulators on chip next to their own TMEM accumulators (3 x 208 x 208 fp32 = 520 KB per CTA for the decoder), so
+// they STAGE the operand tiles (bf16 hi/lo, 4 B/element) and this kernel reduces them: every CTA takes one job and a
+// contiguous range of row tiles (split-K), accumulates a [256 x N] fp32 partial entirely in TMEM (2 M-tiles, up to
+// 2 x 256 columns) and adds it to the global gradient once at the end.
+//
+// Staged layout of a [128 rows x W cols] tile ("k-step major", written by the chain kernels' epilogues):
+//     byte(r, c) = (r / 16) * (2 * W * 32) + [hi: 0 | lo: W * 32] + (c / 8) * 256 + (r % 16) * 16 + (c % 8) * 2
+// i.e. per k-step (16 rows) one contiguous [hi slab][lo slab] pair; inside a slab the 8 contiguous elements run
+// along the OUTPUT dimension, so the slab is consumed directly as an MN-major operand (LBO = 128, SBO = 256).
+#include "common.cuh"
+#include "dw_tc.cuh"
+#include "umma.cuh"
+
+namespace nsdp {
+namespace dwtc {
+
+using namespace umma;
+
+constexpr int STAGES = 4;
+constexpr int THREADS = 6 * 32;  // warp 0 producer, warp 1 MMA, warps 2..5 flush
+constexpr int MAX_JOBS = 16;
+
+struct Params {
+  Job jobs[MAX_JOBS];
+  int njobs;
+  int splits;              // CTAs per job
+  long long tiles;         // row tiles per job (same for all jobs of a launch)
+  int *err;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jid = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const Job job = p.jobs[jid];
+  const long long t0 = p.tiles * split / p.splits, t1 = p.tiles * (split + 1) / p.splits;
+  const uint32_t xs = (uint32_t)job.wx * 32, ys = (uint32_t)job.wy * 32;  // slab bytes
+  const uint32_t stage_bytes = 2 * xs + 2 * ys;
+  const int mtiles = job.wx > 128 ? 2 : 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const bool has_work = t1 > t0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long t = t0; t < t1; ++t) {
+        const unsigned char *xt = job.x + (size_t)t * 512 * job.wx;
+        const unsigned char *yt = job.y + (size_t)t * 512 * job.wy;
+        for (int ks = 0; ks < 8; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1, p.err);
+          mbar_arrive_expect_tx(&full[s], stage_bytes);
+          unsigned char *dst = smem + (size_t)s * stage_bytes;
+          bulk_g2s(dst, xt + (size_t)ks * 2 * xs, 2 * xs, &full[s]);
+          bulk_g2s(dst + 2 * xs, yt + (size_t)ks * 2 * ys, 2 * ys, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = idesc_bf16_mn(128, job.wy);
+      uint32_t it = 0;
+      bool first = true;
+      for (long long t = t0; t < t1; ++t) {
+        for (int ks = 0; ks < 8; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph, p.err);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t yh = smem_desc(sb + 2 * xs, 128, 256), yl = smem_desc(sb + 2 * xs + ys, 128, 256);
+          for (int j = 0; j < mtiles; ++j) {
+            // M-tile j = output rows [128j, 128j+128) = column groups 16j.. of the X slab (4096 bytes further)
+            const uint64_t xh = smem_desc(sb + j * 4096, 128, 256), xl = smem_desc(sb + xs + j * 4096, 128, 256);
+            const uint32_t d = tmem_base + j * 256;
+            mma_bf16(d, xh, yh, idesc, !first);
+            mma_bf16(d, xl, yh, idesc, true);
+            mma_bf16(d, xh, yl, idesc, true);
+          }
+          first = false;
+          mma_commit(&empty[s]);
+        }
+      }
+      mma_commit(&acc_done);
+    }
+  } else if (has_work) {
+    // flush: TMEM lane = output row m, columns = n
+    const int quarter = warp & 3;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    mbar_wait(&acc_done, 0, p.err);
+    tc_fence_after();
+    for (int j = 0; j < mtiles; ++j) {
+      const int m = j * 128 + quarter * 32 + lane;
+      for (int n0 = 0; n0 < job.wy; n0 += 8) {
+        float v[8];
+        tmem_ld8(trow + j * 256 + n0, v);
+        if (m < job.mv) {
+          float *dst = job.out + (size_t)m * job.ldo + n0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (n0 + u < job.nv) atomicAdd(dst + u, v[u]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace dwtc
+
+// Launches the reduction for `njobs` jobs that all span `tiles` row tiles.
+int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cudaStream_t st) {
+  using namespace dwtc;
+  if (njobs <= 0 || njobs > MAX_JOBS || tiles <= 0) return NSDP_ERR_INVALID_ARGUMENT;
+  Params p;
+  int maxw = 0;
+  for (int i = 0; i < njobs; ++i) {
+    p.jobs[i] = jobs[i];
+    if (jobs[i].wx % 16 || jobs[i].wy % 16 || jobs[i].wx > 256 || jobs[i].wy > 256) return NSDP_ERR_UNSUPPORTED;
+    maxw = jobs[i].wx + jobs[i].wy > maxw ? jobs[i].wx + jobs[i].wy : maxw;
+  }
+  p.njobs = njobs;
+  int splits = num_sms() / njobs;
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = (int)tiles;
+  p.splits = splits;
+  p.tiles = tiles;
+  p.err = err;
+  const size_t smem = (size_t)STAGES * 64 * maxw + 4096;  // stage = 2*32*(wx+wy); + slack for the M-tile-1 overrun
+  cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  dw_tc_kernel<<<njobs * splits, THREADS, smem, st>>>(p);
+  return check_launch();
+}
+
+}  // namespace nsdp

@@ -9,7 +9,7 @@ namespace nsdp {
 
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int N, int K,
-                     int split, int *err) {
+                     int split, int mn, int *err) {
   using namespace umma;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -18,19 +18,38 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, f
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
 
-  for (int e = tid; e < 128 * (K / 2); e += 128) {
-    const int row = e / (K / 2), k = (e % (K / 2)) * 2;
-    uint32_t hi, lo;
-    split2(A[row * K + k], A[row * K + k + 1], hi, lo);
-    *reinterpret_cast<uint32_t *>(a_hi + canon_off(128, row, k)) = hi;
-    *reinterpret_cast<uint32_t *>(a_lo + canon_off(128, row, k)) = lo;
-  }
-  for (int e = tid; e < N * (K / 2); e += 128) {
-    const int row = e / (K / 2), k = (e % (K / 2)) * 2;
-    uint32_t hi, lo;
-    split2(B[row * K + k], B[row * K + k + 1], hi, lo);
-    *reinterpret_cast<uint32_t *>(b_hi + canon_off(N, row, k)) = hi;
-    *reinterpret_cast<uint32_t *>(b_lo + canon_off(N, row, k)) = lo;
+  if (!mn) {
+    for (int e = tid; e < 128 * (K / 2); e += 128) {
+      const int row = e / (K / 2), k = (e % (K / 2)) * 2;
+      uint32_t hi, lo;
+      split2(A[row * K + k], A[row * K + k + 1], hi, lo);
+      *reinterpret_cast<uint32_t *>(a_hi + canon_off(128, row, k)) = hi;
+      *reinterpret_cast<uint32_t *>(a_lo + canon_off(128, row, k)) = lo;
+    }
+    for (int e = tid; e < N * (K / 2); e += 128) {
+      const int row = e / (K / 2), k = (e % (K / 2)) * 2;
+      uint32_t hi, lo;
+      split2(B[row * K + k], B[row * K + k + 1], hi, lo);
+      *reinterpret_cast<uint32_t *>(b_hi + canon_off(N, row, k)) = hi;
+      *reinterpret_cast<uint32_t *>(b_lo + canon_off(N, row, k)) = lo;
+    }
+  } else {
+    // operands given as X (K x 128) and Y (K x N): tiles with rows = the reduction index, written exactly like the
+    // K-major kernels write an activation tile, consumed as MN-major operands
+    for (int e = tid; e < K * 64; e += 128) {
+      const int row = e / 64, m = (e % 64) * 2;
+      uint32_t hi, lo;
+      split2(A[row * 128 + m], A[row * 128 + m + 1], hi, lo);
+      *reinterpret_cast<uint32_t *>(a_hi + canon_off(K, row, m)) = hi;
+      *reinterpret_cast<uint32_t *>(a_lo + canon_off(K, row, m)) = lo;
+    }
+    for (int e = tid; e < K * (N / 2); e += 128) {
+      const int row = e / (N / 2), n = (e % (N / 2)) * 2;
+      uint32_t hi, lo;
+      split2(B[row * N + n], B[row * N + n + 1], hi, lo);
+      *reinterpret_cast<uint32_t *>(b_hi + canon_off(K, row, n)) = hi;
+      *reinterpret_cast<uint32_t *>(b_lo + canon_off(K, row, n)) = lo;
+    }
   }
   uint32_t ncols = 32;
   while ((int)ncols < N) ncols *= 2;
@@ -46,7 +65,7 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, f
   const uint32_t tmem_base = tmem_base_s;
 
   if (tid == 0) {
-    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t idesc = mn ? idesc_bf16_mn(128, N) : idesc_bf16(128, N);
     const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
     const int passes = split ? 3 : 1;
     bool acc = false;
@@ -54,8 +73,14 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, f
       const unsigned char *pa = (p == 1) ? a_lo : a_hi;  // hi*hi, lo*hi, hi*lo
       const unsigned char *pb = (p == 2) ? b_lo : b_hi;
       for (int ks = 0; ks < K / 16; ++ks) {
-        const uint64_t ad = smem_desc(smem_u32(pa) + ks * 2 * lbo_a, lbo_a, 128);
-        const uint64_t bd = smem_desc(smem_u32(pb) + ks * 2 * lbo_b, lbo_b, 128);
+        uint64_t ad, bd;
+        if (!mn) {
+          ad = smem_desc(smem_u32(pa) + ks * 2 * lbo_a, lbo_a, 128);
+          bd = smem_desc(smem_u32(pb) + ks * 2 * lbo_b, lbo_b, 128);
+        } else {  // k-step = 16 tile rows = two 128-byte core-matrix rows; column groups are K*16 bytes apart
+          ad = smem_desc(smem_u32(pa) + ks * 256, 128, (uint32_t)K * 16);
+          bd = smem_desc(smem_u32(pb) + ks * 256, 128, (uint32_t)K * 16);
+        }
         mma_bf16(tmem_base, ad, bd, idesc, acc);
         acc = true;
       }
@@ -78,13 +103,14 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, f
 
 }  // namespace nsdp
 
-extern "C" int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int *err, void *stream) {
+extern "C" int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int mn, int *err,
+                                  void *stream) {
   using namespace nsdp;
   if (!A || !B || !D || !err || N < 16 || N > 256 || N % 16 || K < 16 || K % 16) return NSDP_ERR_INVALID_ARGUMENT;
   const size_t smem = 2 * (size_t)(128 + N) * K * 2;
   if (smem > 220 * 1024) return NSDP_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
-  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, split, err);
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, split, mn, err);
   return check_launch();
 }

@@ -97,6 +97,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same, but both operands MN-major (bits 15 / 16): used for "transposed" products D[m][n] = sum_r X[r][m] * Y[r][n]
+// where X and Y are the SAME canonical tiles (row r, column m) the K-major kernels write: seen as an MN-major operand
+// the 8 contiguous elements run along M, the 8 rows of a core matrix along K, so the descriptor takes
+// LBO = 128 (next 8 rows) and SBO = rows*16 (next 8 columns).
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
+  return idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {

@@ -436,15 +436,31 @@ using BCfg256 = BCfg<32, 8, 16, 4, 8>;    // D <= 256: 64 rows
 
 }  // namespace nsdp
 
-extern "C" size_t nsdp_vattn_bwd_workspace_bytes(const nsdp_vattn_args *) { return 0; }
+namespace nsdp {
+size_t vattn_bwd_tc_workspace_bytes(const nsdp_vattn_args *a);
+int vattn_bwd_tc_dispatch(const nsdp_vattn_args *a, const float *out, const float *stats, const float *dout,
+                          const nsdp_vattn_grads *g, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled);
+}
+
+extern "C" size_t nsdp_vattn_bwd_workspace_bytes(const nsdp_vattn_args *args) {
+  if (!args || nsdp::vattn_validate(args) != NSDP_OK || args->impl == 1) return 0;
+  return nsdp::vattn_bwd_tc_workspace_bytes(args);
+}
 
 extern "C" int nsdp_vattn_bwd_f32(const nsdp_vattn_args *args, const float *out, const float *stats, const float *d_out,
-                                  const nsdp_vattn_grads *grads, void *, size_t, void *stream) {
+                                  const nsdp_vattn_grads *grads, void *workspace, size_t workspace_bytes, void *stream) {
   using namespace nsdp;
   int rc = vattn_validate(args);
   if (rc != NSDP_OK) return rc;
-  if (!out || !stats || !d_out || !grads || !args->wd2 || !args->wp || !args->wg2) return NSDP_ERR_INVALID_ARGUMENT;
+  if (!out || !stats || !d_out || !grads) return NSDP_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
+  if (args->impl != 1 && grads->d_wd2t && grads->d_wpt && grads->d_wg2t) {
+    bool handled = false;
+    rc = vattn_bwd_tc_dispatch(args, out, stats, d_out, grads, workspace, workspace_bytes, st, &handled);
+    if (handled) return rc;
+    if (args->impl == 2) return NSDP_ERR_UNSUPPORTED;
+  }
+  if (!args->wd2 || !args->wp || !args->wg2) return NSDP_ERR_INVALID_ARGUMENT;
   const int D = args->D;
   if (D <= 120) return launch_vattn_bwd<BCfg120>(*args, out, stats, d_out, *grads, st);
   if (D <= 128) return launch_vattn_bwd<BCfg128>(*args, out, stats, d_out, *grads, st);

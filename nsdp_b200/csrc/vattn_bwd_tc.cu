@@ -1,0 +1,629 @@
+// Backward of the fused vector attention on tcgen05 tensor cores (sm_100a): the "chain" kernel.
+//
+// Same contract as the CUDA-core backward (vattn_bwd.cu): inputs + forward result + softmax statistics in, every
+// gradient accumulated out; no [pairs, D] activation is ever KEPT. Per tile of 128 pair rows a persistent CTA runs
+//
+//   H -> [gp | dl] (GEMM1) -> G = relu(gp+P) -> a (GEMM2) -> w, s -> ds = w*dout, da = ds*(s-out)
+//     -> dg = da*Wg2 (GEMM3) -> dgp = dg*[g>0] ;  dh = ds*Wd2 (GEMM4a) + dgp*W' (GEMM4b) -> dpre = dh*[h>0]
+//
+// with the same warp roles as the forward kernel (bulk-copy weight producer, single-thread MMA issuer, 16 worker
+// warps that own one TMEM lane = one pair row each). Per-point gradients (d_vp, d_kp, d_qp, d_xyz) are scattered
+// with vector fp32 reductions; d_wd0 / d_bd0 are accumulated per column in registers across all tiles of the CTA.
+//
+// The three d x d weight gradients need 3 x 208 x 208 fp32 of accumulator per CTA, which fits neither TMEM (next to
+// the chain's own 416 columns) nor shared memory. The operand tiles H, G, dA, dGP, dS are therefore STAGED as bf16
+// hi/lo in the k-step-major layout documented in dw_tc.cu and reduced by dw_tc_kernel:
+//     d_wg2t += G^T dA,   d_wpt += H^T dGP,   d_wd2t += H^T dS.
+// The op processes the rows in segments so that the staging workspace stays bounded.
+#include "dw_tc.cuh"
+#include "vattn_tc_common.cuh"
+
+namespace nsdp {
+namespace vtc {
+
+template <class C>
+struct BwdLayout {
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_STAGE = OFF_A + 2 * C::A_HALF;
+  static constexpr int OFF_WD0 = OFF_STAGE + 4 * C::STAGE_BYTES;      // float4[DP]
+  static constexpr int OFF_PC = OFF_WD0 + C::DP * 16;                 // float[DP]
+  static constexpr int OFF_VC = OFF_PC + C::DP * 4;                   // float[DP]
+  static constexpr int OFF_RELS = OFF_VC + C::DP * 4;                 // float4[128]  rel of every row of the tile
+  static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float4[128]  d rel accumulated over the parts
+  static constexpr int OFF_RGV = OFF_RELACC + 128 * 16;               // float[2][DP] per-tile reduction of d_gv
+  static constexpr int OFF_RGQ = OFF_RGV + 2 * C::DP * 4;             // float[2][DP]
+  static constexpr int OFF_BAR = OFF_RGQ + 2 * C::DP * 4;
+  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int SCR_LD = 129;                                  // fp32 scratch [col][129] aliases the A buffer
+  static_assert(C::STAGES == 4, "backward chain kernel assumes a 4-stage ring");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// bytes of one staged [128 x DP] operand tile (hi + lo)
+template <class C>
+constexpr size_t staged_tile_bytes() {
+  return (size_t)512 * C::DP;
+}
+// packed weights: forward regions (GEMM1: 4 slabs / k-step, GEMM2: 2) + three transposed-role regions (2 each)
+template <class C>
+constexpr size_t bwd_packed_bytes() {
+  return (size_t)C::KSTEPS * (4 + 2 + 2 + 2 + 2) * C::SLAB;
+}
+
+template <class C>
+__global__ void pack_bwd_weights_kernel(const float *__restrict__ wpt, const float *__restrict__ wd2t,
+                                        const float *__restrict__ wg2t, int D, unsigned char *__restrict__ out) {
+  // matrices: 0 W' fwd, 1 Wd2 fwd, 2 Wg2 fwd, 3 Wg2 bwd (GEMM3), 4 Wd2 bwd (GEMM4a), 5 W' bwd (GEMM4b)
+  const int per = C::DP * (C::DP / 2);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 6 * per; e += gridDim.x * blockDim.x) {
+    const int m = e / per;
+    const int rem = e - m * per;
+    const int n = rem / (C::DP / 2), k = (rem - n * (C::DP / 2)) * 2;
+    const float *src = (m == 0 || m == 5) ? wpt : ((m == 1 || m == 4) ? wd2t : wg2t);
+    float x0 = 0.f, x1 = 0.f;
+    if (m < 3) {  // forward role: B[n][k] = Wt[k][n]
+      if (n < D && k < D) x0 = src[(size_t)k * D + n];
+      if (n < D && k + 1 < D) x1 = src[(size_t)(k + 1) * D + n];
+    } else {      // backward role: B[n][k] = Wt[n][k]
+      if (n < D && k < D) x0 = src[(size_t)n * D + k];
+      if (n < D && k + 1 < D) x1 = src[(size_t)n * D + k + 1];
+    }
+    uint32_t hi, lo;
+    split2(x0, x1, hi, lo);
+    const int ks = k >> 4;
+    size_t base;
+    if (m < 2)
+      base = (size_t)ks * 4 * C::SLAB + (size_t)m * 2 * C::SLAB;
+    else
+      base = (size_t)C::KSTEPS * (4 + 2 * (m - 2)) * C::SLAB + (size_t)ks * 2 * C::SLAB;
+    const uint32_t in_slab = canon_off(C::DP, n, k & 15);
+    *reinterpret_cast<uint32_t *>(out + base + in_slab) = hi;
+    *reinterpret_cast<uint32_t *>(out + base + C::SLAB + in_slab) = lo;
+  }
+}
+
+struct Staging {
+  unsigned char *h, *g, *da, *dgp, *ds;  // each: tiles_in_segment * staged_tile_bytes
+};
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <class C>
+__device__ __forceinline__ void write_operand(unsigned char *A_hi, unsigned char *A_lo, unsigned char *stage_tile, int r,
+                                              int k0, const float (&x)[8]) {
+  uint4 hi, lo;
+  split2(x[0], x[1], hi.x, lo.x);
+  split2(x[2], x[3], hi.y, lo.y);
+  split2(x[4], x[5], hi.z, lo.z);
+  split2(x[6], x[7], hi.w, lo.w);
+  if (A_hi) {
+    const uint32_t off = canon_off(128, r, k0);
+    *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+    *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+  }
+  if (stage_tile) {  // k-step-major staged layout, see dw_tc.cu
+    unsigned char *p = stage_tile + (size_t)(r >> 4) * (2 * C::DP * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
+    *reinterpret_cast<uint4 *>(p) = hi;
+    *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, const float *__restrict__ stats,
+                    const float *__restrict__ dout, const nsdp_vattn_grads g, const unsigned char *__restrict__ packed,
+                    const Staging stg, long long tile_begin, long long tile_end, int *err) {
+  using L = BwdLayout<C>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + L::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  float *scratch = reinterpret_cast<float *>(smem + L::OFF_A);  // aliases A once GEMM4b has consumed it
+  unsigned char *stage0 = smem + L::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + L::OFF_WD0);
+  float *pcs = reinterpret_cast<float *>(smem + L::OFF_PC);
+  float *vcs = reinterpret_cast<float *>(smem + L::OFF_VC);
+  float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
+  float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
+  float *rgv = reinterpret_cast<float *>(smem + L::OFF_RGV);
+  float *rgq = reinterpret_cast<float *>(smem + L::OFF_RGQ);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + C::STAGES, *a_ready = bars + 2 * C::STAGES, *acc_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const int krows = a.K + (a.has_global ? 1 : 0);
+  const long long BM = (long long)a.B * a.M;
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = 0.f, v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      p = a.pc[kk];
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    pcs[kk] = p;
+    vcs[kk] = v;
+    rgv[kk] = rgv[C::DP + kk] = 0.f;
+    rgq[kk] = rgq[C::DP + kk] = 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_ready, C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t HALF = C::STAGE_BYTES / 2;
+  // byte offsets of the five weight regions inside `packed`
+  constexpr size_t REG1 = 0, REG2 = (size_t)C::KSTEPS * 4 * C::SLAB, REG3 = REG2 + (size_t)C::KSTEPS * 2 * C::SLAB,
+                   REG4 = REG3 + (size_t)C::KSTEPS * 2 * C::SLAB, REG5 = REG4 + (size_t)C::KSTEPS * 2 * C::SLAB;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const size_t reg[5] = {REG1, REG2, REG3, REG4, REG5};
+      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int gi = 0; gi < 5; ++gi) {
+          const uint32_t bytes = gi == 0 ? C::STAGE_BYTES : HALF;
+          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1, err);
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, packed + reg[gi] + (size_t)ks * bytes, bytes, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, C::DP);
+      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo);
+      uint32_t it = 0, ready_phase = 0;
+      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int gi = 0; gi < 5; ++gi) {
+          mbar_wait(a_ready, ready_phase, err);
+          ready_phase ^= 1;
+          tc_fence_after();
+          // destination accumulator / accumulate-into flags of the five GEMMs
+          const uint32_t dcol = (gi == 3 || gi == 4) ? C::ACC1_COL : 0;
+          const bool keep = gi == 4;  // GEMM4b adds to GEMM4a's result
+          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            mbar_wait(&full[s], ph, err);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stage0 + (size_t)s * C::STAGE_BYTES);
+            const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
+            const bool acc = keep || ks > 0;
+            const uint64_t b0h = smem_desc(sb, lbo_b, 128), b0l = smem_desc(sb + C::SLAB, lbo_b, 128);
+            mma_bf16(tmem_base + dcol, ah, b0h, idesc, acc);
+            mma_bf16(tmem_base + dcol, al, b0h, idesc, true);
+            mma_bf16(tmem_base + dcol, ah, b0l, idesc, true);
+            if (gi == 0) {
+              const uint64_t b1h = smem_desc(sb + 2 * C::SLAB, lbo_b, 128), b1l = smem_desc(sb + 3 * C::SLAB, lbo_b, 128);
+              mma_bf16(tmem_base + C::ACC1_COL, ah, b1h, idesc, ks > 0);
+              mma_bf16(tmem_base + C::ACC1_COL, al, b1h, idesc, true);
+              mma_bf16(tmem_base + C::ACC1_COL, ah, b1l, idesc, true);
+            }
+            mma_commit(&empty[s]);
+          }
+          mma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int ww = warp - 2;
+    const int wtid = tid - 64;               // 0 .. 511
+    const int quarter = warp & 3;
+    const int part = ww >> 2;
+    const int r = quarter * 32 + lane;
+    const int ch0 = part * C::CHUNKS / C::NPART, ch1 = (part + 1) * C::CHUNKS / C::NPART;
+    const int nch = ch1 - ch0;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t done_phase = 0;
+    // per-column accumulators of d_wd0 / d_bd0 (worker wtid < D owns column wtid for the whole kernel)
+    float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cb = 0.f;
+
+    auto wait_acc = [&]() {
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+    };
+    auto publish = [&]() {  // operand written -> MMA may start
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    };
+
+    for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      const size_t st_off = (size_t)(tile - tile_begin) * staged_tile_bytes<C>();
+      const RowInfo ri = row_info<C>(a, tile, r, krows);
+      const bool row_on = ri.c >= 0;
+      const bool is_glob = row_on && ri.n < 0;
+      const int b0 = (int)((tile * C::CENTRES) / a.M);                 // batch of the tile's first centre
+      const int bslot = is_glob ? (-ri.n - 1) - b0 : 0;                 // 0 or 1 (tiles span at most 2 shapes if M >= 16)
+      if (part == 0) {
+        rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
+        *reinterpret_cast<float4 *>(relacc + r * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float R[C::MAXCH][8];
+      unsigned long long gmaskbits = 0ull;
+      // ---- H operand (+ staged for d_wpt / d_wd2t) ---------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w0 = wd0s[k0 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
+          }
+          write_operand<C>(A_hi, A_lo, stg.h + st_off, r, k0, h);
+        }
+      }
+      publish();
+      // ---- gather P while GEMM1 runs ---------------------------------------------------------------------------
+      {
+        const float *qrow = (row_on && !is_glob && a.qp) ? a.qp + (size_t)ri.c * D : nullptr;
+        const float *krow = (row_on && !is_glob && a.kp) ? a.kp + (size_t)ri.n * D : nullptr;
+        const float *grow = is_glob ? a.gq + (size_t)(-ri.n - 1) * D : nullptr;
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = (ch0 + q) * 8 + j;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nch && col < D && row_on) {
+              if (grow) {
+                p = ldg4(grow + col);
+              } else {
+                p = *reinterpret_cast<const float4 *>(pcs + col);
+                if (qrow) {
+                  const float4 t = ldg4(qrow + col);
+                  p.x += t.x; p.y += t.y; p.z += t.z; p.w += t.w;
+                }
+                if (krow) {
+                  const float4 t = ldg4(krow + col);
+                  p.x -= t.x; p.y -= t.y; p.z -= t.z; p.w -= t.w;
+                }
+              }
+            }
+            R[q][j] = p.x; R[q][j + 1] = p.y; R[q][j + 2] = p.z; R[q][j + 3] = p.w;
+          }
+        }
+      }
+      // ---- G = relu(gp + P): operand, staging, mask -------------------------------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float v[8], gg[8];
+          tmem_ld8(trow + k0, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gg[j] = (row_on && k0 + j < D) ? fmaxf(v[j] + R[q][j], 0.f) : 0.f;
+            if (gg[j] > 0.f) gmaskbits |= 1ull << (q * 8 + j);
+          }
+          write_operand<C>(A_hi, A_lo, stg.g + st_off, r, k0, gg);
+        }
+      }
+      publish();
+      // ---- gather V while GEMM2 runs ---------------------------------------------------------------------------------
+      {
+        const float *vrow = (row_on && !is_glob && a.vp) ? a.vp + (size_t)ri.n * D : nullptr;
+        const float *gvrow = is_glob ? a.gv + (size_t)(-ri.n - 1) * D : nullptr;
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = (ch0 + q) * 8 + j;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nch && col < D && row_on) {
+              if (gvrow) {
+                t = ldg4(gvrow + col);
+              } else {
+                t = *reinterpret_cast<const float4 *>(vcs + col);
+                if (vrow) {
+                  const float4 u = ldg4(vrow + col);
+                  t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+              }
+            }
+            R[q][j] = t.x; R[q][j + 1] = t.y; R[q][j + 2] = t.z; R[q][j + 3] = t.w;
+          }
+        }
+      }
+      // ---- w, s -> ds = w*dout, da = ds*(s - out); scatter d_vp / d_gv; operand da ------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float av[8], dl[8], ds[8], da[8];
+          tmem_ld8(trow + k0, av);
+          tmem_ld8(trow + C::ACC1_COL + k0, dl);
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = k0 + j;
+            float4 mx = make_float4(0.f, 0.f, 0.f, 0.f), iv = mx, go = mx, o = mx;
+            const bool on = row_on && col < D;
+            if (on) {
+              mx = ldg4(stats + (size_t)ri.c * D + col);
+              iv = ldg4(stats + ((size_t)BM + ri.c) * D + col);
+              go = ldg4(dout + (size_t)ri.c * D + col);
+              o = ldg4(out + (size_t)ri.c * D + col);
+            }
+            const float mxs[4] = {mx.x, mx.y, mx.z, mx.w}, ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+            const float gos[4] = {go.x, go.y, go.z, go.w}, os[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float w = on ? __expf(av[j + u] - mxs[u]) * ivs[u] : 0.f;
+              const float s = is_glob ? R[q][j + u] : R[q][j + u] + dl[j + u];
+              ds[j + u] = w * gos[u];
+              da[j + u] = ds[j + u] * (s - os[u]);
+            }
+            if (on) {
+              if (!is_glob) {
+                if (g.d_vp) red_add_v4(g.d_vp + (size_t)ri.n * D + col, ds[j], ds[j + 1], ds[j + 2], ds[j + 3]);
+              } else if (g.d_gv) {
+                if (bslot < 2) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) atomicAdd(&rgv[bslot * C::DP + col + u], ds[j + u]);
+                } else {
+                  red_add_v4(g.d_gv + (size_t)(-ri.n - 1) * D + col, ds[j], ds[j + 1], ds[j + 2], ds[j + 3]);
+                }
+              }
+            }
+          }
+          write_operand<C>(A_hi, A_lo, stg.da + st_off, r, k0, da);
+          write_operand<C>(nullptr, nullptr, stg.ds + st_off, r, k0, ds);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) R[q][j] = ds[j];
+        }
+      }
+      publish();
+      // ---- GEMM3 done: A is free -> operand ds (GEMM4a) ------------------------------------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) write_operand<C>(A_hi, A_lo, nullptr, r, (ch0 + q) * 8, R[q]);
+      }
+      publish();
+      // ---- dgp = dg * [g > 0] (reads acc0 while GEMM4a fills acc1); scatter d_kp / d_qp / d_gq -------------------------------
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) {
+          const int k0 = (ch0 + q) * 8;
+          float dg[8];
+          tmem_ld8(trow + k0, dg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dg[j] = ((gmaskbits >> (q * 8 + j)) & 1ull) ? dg[j] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int col = k0 + j;
+            if (row_on && col < D) {
+              if (!is_glob) {
+                if (g.d_kp) red_add_v4(g.d_kp + (size_t)ri.n * D + col, -dg[j], -dg[j + 1], -dg[j + 2], -dg[j + 3]);
+                if (g.d_qp) red_add_v4(g.d_qp + (size_t)ri.c * D + col, dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
+              } else if (g.d_gq) {
+                if (bslot < 2) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) atomicAdd(&rgq[bslot * C::DP + col + u], dg[j + u]);
+                } else {
+                  red_add_v4(g.d_gq + (size_t)(-ri.n - 1) * D + col, dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
+                }
+              }
+            }
+          }
+          write_operand<C>(nullptr, nullptr, stg.dgp + st_off, r, k0, dg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) R[q][j] = dg[j];
+        }
+      }
+      // ---- GEMM4a done: A is free -> operand dgp (GEMM4b) ----------------------------------------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < C::MAXCH; ++q) {
+        if (q < nch) write_operand<C>(A_hi, A_lo, nullptr, r, (ch0 + q) * 8, R[q]);
+      }
+      publish();
+      // ---- dpre = dh * [h > 0]; d rel; dpre -> fp32 scratch (aliases A, free once GEMM4b is done) ------------------------------
+      wait_acc();
+      {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+          if (q < nch) {
+            const int k0 = (ch0 + q) * 8;
+            float dh[8];
+            tmem_ld8(trow + C::ACC1_COL + k0, dh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = k0 + j;
+              const float4 w0 = wd0s[col];
+              const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+              const float dp = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
+              sx = fmaf(dp, w0.x, sx); sy = fmaf(dp, w0.y, sy); sz = fmaf(dp, w0.z, sz);
+              if (col < D) scratch[(size_t)col * L::SCR_LD + r] = dp;
+            }
+          }
+        }
+        if (ri.flag != 0.f) {
+          atomicAdd(&relacc[r * 4 + 0], sx);
+          atomicAdd(&relacc[r * 4 + 1], sy);
+          atomicAdd(&relacc[r * 4 + 2], sz);
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // column owners: d_wd0 / d_bd0 partial sums over the 128 rows of the tile
+      if (wtid < D) {
+        const float *colp = scratch + (size_t)wtid * L::SCR_LD;
+#pragma unroll 4
+        for (int rr = 0; rr < 128; ++rr) {
+          const float dp = colp[rr];
+          const float4 rl = rels[rr];
+          cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
+        }
+        // per-tile flush of the global-row reductions
+        if (a.has_global) {
+          for (int sl = 0; sl < 2; ++sl) {
+            const int bb = b0 + sl;
+            if (bb < a.B) {
+              const float v = rgv[sl * C::DP + wtid], qv = rgq[sl * C::DP + wtid];
+              if (g.d_gv && v != 0.f) atomicAdd(g.d_gv + (size_t)bb * D + wtid, v);
+              if (g.d_gq && qv != 0.f) atomicAdd(g.d_gq + (size_t)bb * D + wtid, qv);
+            }
+            rgv[sl * C::DP + wtid] = 0.f;
+            rgq[sl * C::DP + wtid] = 0.f;
+          }
+        }
+      }
+      // row owners: d_xyz
+      if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {
+        const float sx = relacc[r * 4 + 0], sy = relacc[r * 4 + 1], sz = relacc[r * 4 + 2];
+        if (g.d_xyz_c) {
+          float *dst = g.d_xyz_c + (size_t)ri.c * 3;
+          atomicAdd(dst, a.sign * sx); atomicAdd(dst + 1, a.sign * sy); atomicAdd(dst + 2, a.sign * sz);
+        }
+        if (g.d_xyz_n) {
+          float *dst = g.d_xyz_n + (size_t)ri.n * 3;
+          atomicAdd(dst, -a.sign * sx); atomicAdd(dst + 1, -a.sign * sy); atomicAdd(dst + 2, -a.sign * sz);
+        }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    if (wtid < D) {
+      if (g.d_wd0) {
+        atomicAdd(g.d_wd0 + wtid * 3 + 0, cw0); atomicAdd(g.d_wd0 + wtid * 3 + 1, cw1); atomicAdd(g.d_wd0 + wtid * 3 + 2, cw2);
+      }
+      if (g.d_bd0) atomicAdd(g.d_bd0 + wtid, cb);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// tmp (zero-filled scatter target) -> dst += tmp ; colsum[c] += sign * sum_rows tmp[row][c]
+__global__ void finalize_scatter_kernel(const float *__restrict__ tmp, float *__restrict__ dst, float *__restrict__ colsum,
+                                        float sign, long long rows, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float v = tmp[r * D + c];
+    s += v;
+    if (dst) dst[r * D + c] += v;
+  }
+  if (colsum) atomicAdd(colsum + c, sign * s);
+}
+
+constexpr long long kSegmentTiles = 2048;  // staging workspace = 5 tensors x 2048 tiles x 104 KB = 1.06 GB
+
+template <class C>
+static size_t bwd_workspace_bytes(const nsdp_vattn_args &a) {
+  const long long tiles = ceil_div((long long)a.B * a.M, (long long)C::CENTRES);
+  const long long seg = tiles < kSegmentTiles ? tiles : kSegmentTiles;
+  return bwd_packed_bytes<C>() + 256 + 2 * sizeof(float) * (size_t)a.B * a.N * a.D + 5 * (size_t)seg * staged_tile_bytes<C>();
+}
+
+template <class C>
+static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *stats, const float *dout,
+                      const nsdp_vattn_grads &g, void *workspace, size_t ws_bytes, cudaStream_t st) {
+  if (!workspace || ws_bytes < bwd_workspace_bytes<C>(a)) return NSDP_ERR_WORKSPACE;
+  if (!g.d_wd2t || !g.d_wpt || !g.d_wg2t) return NSDP_ERR_INVALID_ARGUMENT;
+  unsigned char *packed = (unsigned char *)workspace;
+  int *err = (int *)(packed + bwd_packed_bytes<C>());
+  // d_vp / d_kp are scattered into zeroed temporaries so that d_vc = sum d_vp and d_pc = -sum d_kp (the bias
+  // gradients are column sums over the non-global rows, which is exactly what lands in those tables) can be derived
+  // without touching whatever running sum the caller keeps in its own buffers
+  const size_t tbl = (size_t)a.B * a.N * a.D;
+  float *tmp_vp = (float *)(packed + bwd_packed_bytes<C>() + 256);
+  float *tmp_kp = tmp_vp + tbl;
+  unsigned char *stage_base = (unsigned char *)(tmp_kp + tbl);
+  const long long tiles = ceil_div((long long)a.B * a.M, (long long)C::CENTRES);
+  const long long seg = tiles < kSegmentTiles ? tiles : kSegmentTiles;
+  const size_t per = (size_t)seg * staged_tile_bytes<C>();
+  Staging stg{stage_base, stage_base + per, stage_base + 2 * per, stage_base + 3 * per, stage_base + 4 * per};
+  cudaError_t e = cudaMemsetAsync(err, 0, 256 + 2 * tbl * sizeof(float), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  nsdp_vattn_grads gk = g;   // what the kernel scatters into
+  gk.d_vp = tmp_vp;
+  gk.d_kp = tmp_kp;
+  pack_bwd_weights_kernel<C><<<96, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
+  int rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  auto kern = vattn_bwd_tc_kernel<C>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<C>::SMEM);
+  if (e != cudaSuccess) return cuda_rc(e);
+  for (long long t0 = 0; t0 < tiles; t0 += seg) {
+    const long long t1 = t0 + seg < tiles ? t0 + seg : tiles;
+    const long long n = t1 - t0;
+    const int grid = (int)(n < num_sms() ? n : num_sms());
+    kern<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, gk, packed, stg, t0, t1, err);
+    rc = check_launch();
+    if (rc != NSDP_OK) return rc;
+    dwtc::Job jobs[3] = {
+        {stg.g, stg.da, g.d_wg2t, C::DP, C::DP, a.D, a.D, a.D},
+        {stg.h, stg.dgp, g.d_wpt, C::DP, C::DP, a.D, a.D, a.D},
+        {stg.h, stg.ds, g.d_wd2t, C::DP, C::DP, a.D, a.D, a.D},
+    };
+    rc = dw_tc_launch(jobs, 3, n, err, st);
+    if (rc != NSDP_OK) return rc;
+  }
+  const long long rows = (long long)a.B * a.N;
+  dim3 fgrid((unsigned)ceil_div(a.D, 128), (unsigned)(rows < 64 ? rows : 64));
+  finalize_scatter_kernel<<<fgrid, 128, 0, st>>>(tmp_vp, a.vp ? g.d_vp : nullptr, g.d_vc, 1.f, rows, a.D);
+  finalize_scatter_kernel<<<fgrid, 128, 0, st>>>(tmp_kp, a.kp ? g.d_kp : nullptr, g.d_pc, -1.f, rows, a.D);
+  return check_launch();
+}
+
+static int pick_bwd(const nsdp_vattn_args &a) {
+  const int krows = a.K + (a.has_global ? 1 : 0);
+  if (a.D % 4 != 0) return 0;
+  if (a.D <= 204 && a.D > 128 && krows == 8 && a.M >= 16 && a.kp && a.vp) return 1;
+  return 0;
+}
+
+}  // namespace vtc
+
+size_t vattn_bwd_tc_workspace_bytes(const nsdp_vattn_args *a) {
+  switch (vtc::pick_bwd(*a)) {
+    case 1: return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8>>(*a);
+    default: return 0;
+  }
+}
+
+int vattn_bwd_tc_dispatch(const nsdp_vattn_args *a, const float *out, const float *stats, const float *dout,
+                          const nsdp_vattn_grads *g, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled) {
+  *handled = true;
+  switch (vtc::pick_bwd(*a)) {
+    case 1: return vtc::launch_bwd<vtc::TcCfg<208, 8>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    default: *handled = false; return NSDP_OK;
+  }
+}
+
+}  // namespace nsdp

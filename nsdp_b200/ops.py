@@ -303,9 +303,13 @@ class _VectorAttention(torch.autograd.Function):
         gs = VattnGrads()
         for n, t in g.items():
             setattr(gs, n, _p(t))
-        with torch.cuda.device(d_out.device), _timed(f"vattn_bwd_D{a.D}_K{a.K}_M{a.M}"):
-            check(_lib.lib().nsdp_vattn_bwd_f32(C.byref(a), out.data_ptr(), stats.data_ptr(), d_out.data_ptr(), C.byref(gs),
-                                                None, 0, _stream()), "nsdp_vattn_bwd_f32")
+        L = _lib.lib()
+        with torch.cuda.device(d_out.device):
+            ws_bytes = L.nsdp_vattn_bwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
+            with _timed(f"vattn_bwd_D{a.D}_K{a.K}_M{a.M}"):
+                check(L.nsdp_vattn_bwd_f32(C.byref(a), out.data_ptr(), stats.data_ptr(), d_out.data_ptr(), C.byref(gs),
+                                           _p(ws), ws_bytes, _stream()), "nsdp_vattn_bwd_f32")
         _count()
         return (g["d_xyz_c"], g["d_xyz_n"], None, g["d_qp"], g["d_kp"], g["d_vp"], g["d_gq"], g["d_gv"], g["d_wd0"],
                 g["d_bd0"], g["d_wd2t"], g["d_wpt"], g["d_wg2t"], g["d_pc"], g["d_vc"], None)

@@ -8,14 +8,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _run(N, K, split, seed=0):
+def _run(N, K, split, seed=0, mn=0):
     g = torch.Generator().manual_seed(seed)
-    A = torch.randn(128, K, generator=g)
-    B = torch.randn(N, K, generator=g)
+    A = torch.randn(K, 128, generator=g) if mn else torch.randn(128, K, generator=g)
+    B = torch.randn(K, N, generator=g) if mn else torch.randn(N, K, generator=g)
     Ad, Bd = A.to(DEV), B.to(DEV)
     D = torch.zeros(128, N, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    rc = _lib.lib().nsdp_selftest_umma(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split, err.data_ptr(),
+    rc = _lib.lib().nsdp_selftest_umma(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split, mn, err.data_ptr(),
                                        torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "nsdp_selftest_umma")
     torch.cuda.synchronize()
@@ -36,3 +36,12 @@ def test_umma_bf16x3_is_fp32_grade(N, K):
     want = A.double() @ B.double().t()
     rel = ((D.double() - want).norm() / want.norm()).item()
     assert rel < 3e-5, rel   # plain bf16 is ~3e-3 here
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (208, 128), (256, 64), (128, 128)])
+def test_umma_mn_major_operands(N, K):
+    """D = X^T Y with X (K,128), Y (K,N) stored as row tiles and consumed as MN-major operands."""
+    X, Y, D = _run(N, K, 1, seed=7, mn=1)
+    want = X.double().t() @ Y.double()
+    rel = ((D.double() - want).norm() / want.norm()).item()
+    assert rel < 3e-5, rel
