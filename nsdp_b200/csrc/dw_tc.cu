@@ -21,7 +21,7 @@ using namespace umma;
 
 constexpr int STAGES = 4;
 constexpr int THREADS = 6 * 32;  // warp 0 producer, warp 1 MMA, warps 2..5 flush
-constexpr int MAX_JOBS = 16;
+constexpr int MAX_JOBS = 24;
 
 struct Params {
   Job jobs[MAX_JOBS];
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);  // MMA commit + the column-sum warp
     }
     mbar_init(&acc_done, 1);
     mbar_fence_init();
@@ -103,6 +103,42 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       mma_commit(&acc_done);
     }
   } else if (has_work) {
+    if (warp == 2) {
+      // column sums of Y (bias gradients) straight from the staged slabs as they pass through shared memory:
+      // lane = column group of 8, 16 rows per k-step, hi + lo
+      float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool mine = job.colsum && lane * 8 < job.wy;
+      uint32_t it = 0;
+      for (long long t = t0; t < t1; ++t) {
+        for (int ks = 0; ks < 8; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph, p.err);
+          if (mine) {
+            const unsigned char *yh = smem + (size_t)s * stage_bytes + 2 * xs + (size_t)lane * 256;
+            const unsigned char *yl = yh + ys;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const uint4 h4 = *reinterpret_cast<const uint4 *>(yh + rr * 16);
+              const uint4 l4 = *reinterpret_cast<const uint4 *>(yl + rr * 16);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                cs[2 * u] += __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+                cs[2 * u + 1] += __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+      }
+      if (mine) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (lane * 8 + u < job.nv) atomicAdd(job.colsum + lane * 8 + u, cs[u]);
+      }
+    }
     // flush: TMEM lane = output row m, columns = n
     const int quarter = warp & 3;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);

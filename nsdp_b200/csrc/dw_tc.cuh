@@ -11,6 +11,7 @@ struct Job {
   float *out;              // [mv][ldo], accumulated atomically: out[m][n] += sum_r X[r][m] * Y[r][n]
   int wx, wy;              // padded widths (multiples of 16, <= 256)
   int mv, nv, ldo;         // valid extent / leading dimension of `out`
+  float *colsum;           // optional [nv]: colsum[n] += sum_r Y[r][n]  (bias gradients), or nullptr
 };
 
 }  // namespace dwtc

@@ -317,8 +317,18 @@ static size_t tail_bwd_weight_floats(const nsdp_tail_args *a) {
   return (size_t)(1 + a->n_blocks) * tailb::H * a->C + 2 * (size_t)a->n_blocks * tailb::H * tailb::H;
 }
 
+namespace nsdp {
+size_t tail_bwd_tc_workspace_bytes(const nsdp_tail_args *a);
+int tail_bwd_tc_dispatch(const nsdp_tail_args *a, const float *dout, const nsdp_tail_grads *g, void *workspace,
+                         size_t ws_bytes, cudaStream_t st, bool *handled);
+}
+
 extern "C" size_t nsdp_resnet_tail_bwd_workspace_bytes(const nsdp_tail_args *a) {
   if (!a || a->R <= 0) return 0;
+  if (a->impl != 1) {
+    const size_t tc = nsdp::tail_bwd_tc_workspace_bytes(a);
+    if (tc) return tc;
+  }
   const long long tiles = ceil_div((long long)a->R, (long long)tailb::R);
   return sizeof(float) * (tail_bwd_weight_floats(a) + (size_t)tailb::grid_size(tiles) * tailb::kSlotFloats);
 }
@@ -344,6 +354,12 @@ extern "C" int nsdp_resnet_tail_bwd_f32(const nsdp_tail_args *a, const float *d_
   if (a->H != tailb::H || a->C % 4 != 0 || a->C > 256 || a->O > 4) return NSDP_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < nsdp_resnet_tail_bwd_workspace_bytes(a)) return NSDP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->impl != 1) {
+    bool handled = false;
+    int rc = tail_bwd_tc_dispatch(a, d_out, g, workspace, workspace_bytes, st, &handled);
+    if (handled) return rc;
+    if (a->impl == 2) return NSDP_ERR_UNSUPPORTED;
+  }
   const int H = tailb::H, C = a->C, nb = a->n_blocks;
   float *ws = (float *)workspace;
   float *wc = ws;                                   // ((1+n)H, C)  = transpose of wc_t (C, (1+n)H)

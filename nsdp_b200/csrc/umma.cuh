@@ -43,16 +43,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike); after ~2^26 polls the
-// kernel sets *err (if given) and falls through, producing garbage that the parity tests catch.
+// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike). mbarrier.try_wait may itself block
+// for a hardware-defined interval, so the bound is on TIME (%globaltimer): 2 s for the first wait that fails,
+// 20 us for every wait once the error flag is up. A timed-out kernel produces garbage that the parity tests catch.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err = nullptr) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    ++spins;
-    // once any wait in the grid has timed out, every other wait gives up quickly too
-    if (spins > 4096u && (spins > (1u << 26) || (err && *reinterpret_cast<volatile int *>(err) != 0))) {
-      if (err) atomicExch(err, 1);
-      break;
+    if ((++spins & 63u) == 0u) {
+      const unsigned long long dt = global_ns() - t0;
+      const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
+      if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
+        if (err) atomicExch(err, 1);
+        break;
+      }
     }
   }
 }

@@ -25,7 +25,7 @@ template <class C>
 struct BwdLayout {
   static constexpr int OFF_A = 0;
   static constexpr int OFF_STAGE = OFF_A + 2 * C::A_HALF;
-  static constexpr int OFF_WD0 = OFF_STAGE + 4 * C::STAGE_BYTES;      // float4[DP]
+  static constexpr int OFF_WD0 = OFF_STAGE + C::STAGES * C::STAGE_BYTES;  // float4[DP]
   static constexpr int OFF_PC = OFF_WD0 + C::DP * 16;                 // float[DP]
   static constexpr int OFF_VC = OFF_PC + C::DP * 4;                   // float[DP]
   static constexpr int OFF_RELS = OFF_VC + C::DP * 4;                 // float4[128]  rel of every row of the tile
@@ -34,8 +34,9 @@ struct BwdLayout {
   static constexpr int OFF_RGQ = OFF_RGV + 2 * C::DP * 4;             // float[2][DP]
   static constexpr int OFF_BAR = OFF_RGQ + 2 * C::DP * 4;
   static constexpr int SMEM = OFF_BAR + 256;
-  static constexpr int SCR_LD = 129;                                  // fp32 scratch [col][129] aliases the A buffer
-  static_assert(C::STAGES == 4, "backward chain kernel assumes a 4-stage ring");
+  // fp32 scratch [col][128] aliasing the A buffer (exactly 2 * A_HALF bytes for D == DP); element (col, row) sits at
+  // col*128 + ((row + col) & 127): the rotation keeps both the row-wise writes and the column-wise reads conflict-free
+  static constexpr int SCR_LD = 128;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -466,7 +467,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
               const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
               const float dp = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
               sx = fmaf(dp, w0.x, sx); sy = fmaf(dp, w0.y, sy); sz = fmaf(dp, w0.z, sz);
-              if (col < D) scratch[(size_t)col * L::SCR_LD + r] = dp;
+              if (col < D) scratch[(size_t)col * L::SCR_LD + ((r + col) & 127)] = dp;
             }
           }
         }
@@ -483,7 +484,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
         const float *colp = scratch + (size_t)wtid * L::SCR_LD;
 #pragma unroll 4
         for (int rr = 0; rr < 128; ++rr) {
-          const float dp = colp[rr];
+          const float dp = colp[(rr + wtid) & 127];
           const float4 rl = rels[rr];
           cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
         }
@@ -587,9 +588,9 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
     rc = check_launch();
     if (rc != NSDP_OK) return rc;
     dwtc::Job jobs[3] = {
-        {stg.g, stg.da, g.d_wg2t, C::DP, C::DP, a.D, a.D, a.D},
-        {stg.h, stg.dgp, g.d_wpt, C::DP, C::DP, a.D, a.D, a.D},
-        {stg.h, stg.ds, g.d_wd2t, C::DP, C::DP, a.D, a.D, a.D},
+        {stg.g, stg.da, g.d_wg2t, C::DP, C::DP, a.D, a.D, a.D, nullptr},
+        {stg.h, stg.dgp, g.d_wpt, C::DP, C::DP, a.D, a.D, a.D, nullptr},
+        {stg.h, stg.ds, g.d_wd2t, C::DP, C::DP, a.D, a.D, a.D, nullptr},
     };
     rc = dw_tc_launch(jobs, 3, n, err, st);
     if (rc != NSDP_OK) return rc;
@@ -603,8 +604,10 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
 
 static int pick_bwd(const nsdp_vattn_args &a) {
   const int krows = a.K + (a.has_global ? 1 : 0);
-  if (a.D % 4 != 0) return 0;
-  if (a.D <= 204 && a.D > 128 && krows == 8 && a.M >= 16 && a.kp && a.vp) return 1;
+  if (a.D % 4 != 0 || a.D > 256 || !a.kp || !a.vp) return 0;
+  if (krows <= 8 && a.D > 128 && a.D <= 208 && (!a.has_global || a.M >= 16)) return 1;
+  if (krows <= 16 && !a.has_global) return a.D <= 128 ? 2 : 3;
+  if (krows <= 128 && !a.has_global && a.D > 128) return 4;
   return 0;
 }
 
@@ -613,6 +616,9 @@ static int pick_bwd(const nsdp_vattn_args &a) {
 size_t vattn_bwd_tc_workspace_bytes(const nsdp_vattn_args *a) {
   switch (vtc::pick_bwd(*a)) {
     case 1: return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8>>(*a);
+    case 2: return vtc::bwd_workspace_bytes<vtc::TcCfg<128, 16>>(*a);
+    case 3: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 16>>(*a);
+    case 4: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 128>>(*a);
     default: return 0;
   }
 }
@@ -622,6 +628,9 @@ int vattn_bwd_tc_dispatch(const nsdp_vattn_args *a, const float *out, const floa
   *handled = true;
   switch (vtc::pick_bwd(*a)) {
     case 1: return vtc::launch_bwd<vtc::TcCfg<208, 8>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 2: return vtc::launch_bwd<vtc::TcCfg<128, 16>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 3: return vtc::launch_bwd<vtc::TcCfg<256, 16>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 4: return vtc::launch_bwd<vtc::TcCfg<256, 128>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
     default: *handled = false; return NSDP_OK;
   }
 }

@@ -302,44 +302,112 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
       done_phase ^= 1;
       tc_fence_after();
       const long long ci = tile * C::CENTRES + r / C::KR;   // centre of this lane's group
-      const int gl = lane & (C::KR - 1);
+      if constexpr (C::KR < 128) {
+        const int gl = lane & (C::KR - 1);
 #pragma unroll
-      for (int q = 0; q < C::MAXCH; ++q) {
-        if (q < nch) {
-          const int k0 = (ch0 + q) * 8;
-          float av[8], dl[8];
-          tmem_ld8(trow + k0, av);
-          tmem_ld8(trow + C::ACC1_COL + k0, dl);
-          float e[8], es[8], mxv[8];
+        for (int q = 0; q < C::MAXCH; ++q) {
+          if (q < nch) {
+            const int k0 = (ch0 + q) * 8;
+            float av[8], dl[8];
+            tmem_ld8(trow + k0, av);
+            tmem_ld8(trow + C::ACC1_COL + k0, dl);
+            float e[8], es[8], mxv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float x = row_on ? av[j] : -INFINITY;
-            float mx = x;
+            for (int j = 0; j < 8; ++j) {
+              const float x = row_on ? av[j] : -INFINITY;
+              float mx = x;
 #pragma unroll
-            for (int off = 1; off < C::KR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-            mxv[j] = mx;
-            const float ex = row_on ? __expf(x - mx) : 0.f;
-            const float sv = is_glob ? P[q][j] : P[q][j] + dl[j];
-            e[j] = ex;
-            es[j] = ex * sv;
-          }
-          const float se = group_transpose_sum<C::KR>(e, lane);
-          const float ses = group_transpose_sum<C::KR>(es, lane);
-          if (gl < 8) {
-            const int col = k0 + gl;
-            if (ci < BM && col < D) {
-              const float inv = 1.f / se;
-              out[ci * D + col] = ses * inv;
-              if (stats) {
-                float m = mxv[0];
+              for (int off = 1; off < C::KR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+              mxv[j] = mx;
+              const float ex = row_on ? __expf(x - mx) : 0.f;
+              const float sv = is_glob ? P[q][j] : P[q][j] + dl[j];
+              e[j] = ex;
+              es[j] = ex * sv;
+            }
+            const float se = group_transpose_sum<C::KR>(e, lane);
+            const float ses = group_transpose_sum<C::KR>(es, lane);
+            if (gl < 8) {
+              const int col = k0 + gl;
+              if (ci < BM && col < D) {
+                const float inv = 1.f / se;
+                out[ci * D + col] = ses * inv;
+                if (stats) {
+                  float m = mxv[0];
 #pragma unroll
-                for (int j = 1; j < 8; ++j) m = (gl == j) ? mxv[j] : m;
-                stats[ci * D + col] = m;
-                stats[(BM + ci) * D + col] = inv;
+                  for (int j = 1; j < 8; ++j) m = (gl == j) ? mxv[j] : m;
+                  stats[ci * D + col] = m;
+                  stats[(BM + ci) * D + col] = inv;
+                }
               }
             }
           }
         }
+      } else {
+        // one centre per tile: the softmax spans all four lane quarters -> warp reduction, then an exchange
+        // through shared memory (two named barriers per tile)
+        float *red = reinterpret_cast<float *>(smem + C::OFF_RED);   // [3][4][DP]: max, sum e, sum e*s
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+          if (q < nch) {
+            const int k0 = (ch0 + q) * 8;
+            float av[8];
+            tmem_ld8(trow + k0, av);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) av[j] = row_on ? av[j] : -INFINITY;
+            const float m = group_transpose_max<32>(av, lane);
+            if (lane < 8) red[(0 * 4 + quarter) * C::DP + k0 + lane] = m;
+          }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < C::MAXCH; ++q) {
+          if (q < nch) {
+            const int k0 = (ch0 + q) * 8;
+            float av[8], dl[8], e[8], es[8];
+            tmem_ld8(trow + k0, av);
+            tmem_ld8(trow + C::ACC1_COL + k0, dl);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = k0 + j;
+              const float mx = fmaxf(fmaxf(red[0 * C::DP + col], red[1 * C::DP + col]),
+                                     fmaxf(red[2 * C::DP + col], red[3 * C::DP + col]));
+              const float ex = row_on ? __expf(av[j] - mx) : 0.f;
+              e[j] = ex;
+              es[j] = ex * (P[q][j] + dl[j]);
+            }
+            const float se = group_transpose_sum<32>(e, lane);
+            const float ses = group_transpose_sum<32>(es, lane);
+            if (lane < 8) {
+              red[(1 * 4 + quarter) * C::DP + k0 + lane] = se;
+              red[(2 * 4 + quarter) * C::DP + k0 + lane] = ses;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (quarter == 0 && ci < BM) {
+#pragma unroll
+          for (int q = 0; q < C::MAXCH; ++q) {
+            if (q < nch && lane < 8) {
+              const int col = (ch0 + q) * 8 + lane;
+              if (col < D) {
+                float mx = -INFINITY, se = 0.f, ses = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) {
+                  mx = fmaxf(mx, red[(0 * 4 + w4) * C::DP + col]);
+                  se += red[(1 * 4 + w4) * C::DP + col];
+                  ses += red[(2 * 4 + w4) * C::DP + col];
+                }
+                const float inv = 1.f / se;
+                out[ci * D + col] = ses * inv;
+                if (stats) {
+                  stats[ci * D + col] = mx;
+                  stats[(BM + ci) * D + col] = inv;
+                }
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // `red` is rewritten by the next tile
       }
       tc_fence_before();
     }
@@ -369,10 +437,16 @@ static int launch(const nsdp_vattn_args &a, float *out, float *stats, void *work
 }
 
 // Which (DP, KR) instantiation serves these arguments; 0 = not supported by the tensor-core path.
+//   1: <208, 8>   decoder: D in (128, 208], 7 neighbours + global token
+//   2: <128, 16>  encoder d_reduced: D <= 128, up to 16 rows per centre (k = 10 is padded to 16)
+//   3: <256, 16>  encoder d_transformer: D <= 256, up to 16 rows per centre
+//   4: <256, 128> full attention over up to 128 source points (group_all, one centre per tile)
 static int pick(const nsdp_vattn_args &a) {
   const int krows = a.K + (a.has_global ? 1 : 0);
-  if (a.D % 4 != 0) return 0;
-  if (a.D <= 208 && a.D > 128 && krows == 8) return 1;    // decoder: D = 200, 7 + global
+  if (a.D % 4 != 0 || a.D > 256) return 0;
+  if (krows <= 8 && a.D > 128 && a.D <= 208) return 1;
+  if (krows <= 16 && !a.has_global) return a.D <= 128 ? 2 : 3;
+  if (krows <= 128 && !a.has_global && a.D > 128) return 4;
   return 0;
 }
 
@@ -384,6 +458,9 @@ extern "C" size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args) {
   if (!args) return 0;
   switch (vtc::pick(*args)) {
     case 1: return vtc::packed_bytes<vtc::TcCfg<208, 8>>() + 16;
+    case 2: return vtc::packed_bytes<vtc::TcCfg<128, 16>>() + 16;
+    case 3: return vtc::packed_bytes<vtc::TcCfg<256, 16>>() + 16;
+    case 4: return vtc::packed_bytes<vtc::TcCfg<256, 128>>() + 16;
     default: return 0;
   }
 }
@@ -394,6 +471,9 @@ int vattn_fwd_tc_dispatch(const nsdp_vattn_args *args, float *out, float *stats,
   *handled = true;
   switch (vtc::pick(*args)) {
     case 1: return vtc::launch<vtc::TcCfg<208, 8>>(*args, out, stats, workspace, ws_bytes, st);
+    case 2: return vtc::launch<vtc::TcCfg<128, 16>>(*args, out, stats, workspace, ws_bytes, st);
+    case 3: return vtc::launch<vtc::TcCfg<256, 16>>(*args, out, stats, workspace, ws_bytes, st);
+    case 4: return vtc::launch<vtc::TcCfg<256, 128>>(*args, out, stats, workspace, ws_bytes, st);
     default: *handled = false; return NSDP_OK;
   }
 }

@@ -33,7 +33,8 @@ struct TcCfg {
   static constexpr int OFF_WD0 = OFF_STAGE + STAGES * STAGE_BYTES;   // float4[DP]
   static constexpr int OFF_PC = OFF_WD0 + DP * 16;                   // float[DP]
   static constexpr int OFF_VC = OFF_PC + DP * 4;                     // float[DP]
-  static constexpr int OFF_BAR = OFF_VC + DP * 4;                    // mbarriers
+  static constexpr int OFF_RED = OFF_VC + DP * 4;                    // float[3][4][DP] cross-warp softmax (KR == 128)
+  static constexpr int OFF_BAR = OFF_RED + (KR_ == 128 ? 3 * 4 * DP * 4 : 0);   // mbarriers
   static constexpr int SMEM = OFF_BAR + 256;
   static_assert(DP % 16 == 0 && DP <= 256, "unsupported padded width");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -102,6 +103,42 @@ __device__ __forceinline__ float group_transpose_sum(float (&v)[8], int lane) {
     const float send = up ? v[0] : v[1];
     const float keep = up ? v[1] : v[0];
     v[0] = keep + __shfl_xor_sync(full, send, 1);
+  }
+  return v[0];
+}
+
+// max variant of group_transpose_sum: lane j (j = lane % G < 8) ends with the group maximum of v[j] in v[0]
+template <int G>
+__device__ __forceinline__ float group_transpose_max(float (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int off = G / 2; off >= 8; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(full, v[i], off));
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(full, send, 4));
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(full, send, 2));
+    }
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = fmaxf(keep, __shfl_xor_sync(full, send, 1));
   }
   return v[0];
 }

@@ -71,10 +71,21 @@ def test_forward_against_oracle_multi_shape_fp16_grid(schemas):
     assert _mean_l2(got.cpu().numpy(), want.numpy()) < TOL
 
 
-def test_training_step_against_reference_golden(golden, schemas):
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-cuda-cores", "auto-tcgen05"])
+def test_training_step_against_reference_golden(golden, schemas, impl, monkeypatch):
     """fwd + bwd through the CUDA kernels (train-mode BatchNorm): loss, prediction, d/d query coordinates,
     d/d surface inputs, selected parameter gradients, all gradient norms and BN running stats vs the live
-    reference (tests/golden/make_golden.py, 'train_fwd_*')."""
+    reference (tests/golden/make_golden.py, 'train_fwd_*').
+
+    Gradient bar: relative L2 < 1e-3 on the fp32 CUDA-core kernels. The tensor-core kernels (bf16x3) reproduce
+    pre-activations to ~3e-6 instead of ~1e-7, which flips the ReLU mask of the few elements that sit within ~1e-5 of
+    the kink (tests/test_gpu_vattn.py::_tc_grad_ok; reproduced by a CPU emulation of the arithmetic); the gradients
+    that sum over those elements move by ~1e-3 (measured: d/d query 1.1e-3), so that path is held to 5e-3. The
+    forward tolerance (flow < 1e-4) is the same on both."""
+    from nsdp_b200 import ops
+    monkeypatch.setattr(ops, "VATTN_IMPL", impl)
+    monkeypatch.setattr(ops, "TAIL_IMPL", impl)
+    gtol = 1e-3 if impl == 1 else 5e-3
     model = _model(schemas, "forward").train()
     b = synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
     q = b["space_samples_src"].to(DEV).requires_grad_(True)
@@ -86,13 +97,13 @@ def test_training_step_against_reference_golden(golden, schemas):
     assert abs(loss.item() - float(golden["train_fwd_loss"])) < 1e-5
     assert _mean_l2(pred.detach().cpu().numpy(), golden["train_fwd_pred"]) < TOL
     rel = lambda a, ref: float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30))
-    assert rel(q.grad.cpu().numpy(), golden["train_fwd_dq"]) < 1e-3
-    assert rel(surf.grad.cpu().numpy(), golden["train_fwd_dsurf"]) < 1e-3
+    assert rel(q.grad.cpu().numpy(), golden["train_fwd_dq"]) < gtol
+    assert rel(surf.grad.cpu().numpy(), golden["train_fwd_dsurf"]) < gtol
     grads = {k: p.grad for k, p in model.named_parameters()}
     for key in golden.files:
         if key.startswith("train_fwd_grad::"):
             k = key.split("::", 1)[1]
-            assert rel(grads[k].cpu().numpy(), golden[key]) < 1e-3, k
+            assert rel(grads[k].cpu().numpy(), golden[key]) < gtol, k
         if key.startswith("train_fwd_buf::"):
             k = key.split("::", 1)[1]
             np.testing.assert_allclose(model.state_dict()[k].cpu().numpy(), golden[key], atol=1e-5, rtol=1e-4)
@@ -106,7 +117,7 @@ def test_training_step_against_reference_golden(golden, schemas):
             assert r < 1e-6 and (a <= 1e-6)
             continue
         # parameters feeding straight into a BatchNorm (e.g. a bias) have a true gradient of 0: both sides are noise
-        assert abs(a - r) <= 2e-3 * r + 1e-7, (n, a, r)
+        assert abs(a - r) <= 2 * gtol * r + 1e-7, (n, a, r)
 
 
 def test_flow_arbitrary_training_step(golden, schemas):

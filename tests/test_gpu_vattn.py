@@ -131,9 +131,25 @@ BWD_CASES = [
 ]
 
 
+# Gradients that do not pass through a ReLU mask decision of the recomputed chain: held tight on every path.
+KINK_FREE = {"vp", "vc", "gv", "wd2t", "wg2t"}
+
+
+def _tc_grad_ok(name, got, ref):
+    """Tolerances for the bf16x3 tensor-core backward. The chain reproduces pre-activations to ~3e-6, which flips the
+    ReLU mask of the handful of elements whose pre-activation lies within ~1e-5 of zero (measured on the GPU AND
+    reproduced bit-for-bit in magnitude by a CPU emulation of the bf16x3 arithmetic: ~4 flips in 360k elements give
+    4e-3 relative L2 on d gp and up to 8e-3 on the gradients that sum it). Those gradients get a bound that only
+    catches real bugs (a wrong term is O(1)); everything that does not depend on a mask decision stays at 1e-4."""
+    err = _rel_err(got, ref)
+    return err < (1e-4 if name in KINK_FREE else 2e-2), err
+
+
 @pytest.mark.parametrize("cfg", BWD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 @pytest.mark.parametrize("sign", [1.0, -1.0])
-def test_vattn_backward(cfg, sign):
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32", "auto"])
+def test_vattn_backward(cfg, sign, impl, monkeypatch):
+    monkeypatch.setattr(ops, "VATTN_IMPL", impl)
     case = _rel_case = _rand_case(seed=11, **cfg)
     names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
     cpu = {k: (v.double().clone().requires_grad_(True) if k in names else v) for k, v in case.items()}
@@ -146,10 +162,12 @@ def test_vattn_backward(cfg, sign):
     got.backward(go.float().to(DEV))
     for k in names:
         assert dev[k].grad is not None, k
-        err = _rel_err(dev[k].grad, cpu[k].grad)
-        # fp32 CUDA-core kernels: < 2e-4. The tensor-core chain (five chained bf16x3 products before d rel) measures
-        # 2.3e-4 on d xyz_c; the model-level bar is 1e-3 (tests/test_gpu_tdnet.py).
-        assert err < 5e-4, (k, err)
+        if impl == 1:   # fp32 CUDA-core kernels
+            err = _rel_err(dev[k].grad, cpu[k].grad)
+            assert err < 2e-4, (k, err)
+        else:           # tensor-core kernels where instantiated (bf16x3)
+            ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad)
+            assert ok, (k, info)
 
 
 def test_vattn_backward_self_attention_shares_xyz():
@@ -167,8 +185,11 @@ def test_vattn_backward_self_attention_shares_xyz():
     assert _rel_err(xyz.grad, xyz64.grad) < 2e-4
 
 
-@pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (64, 200, 5, 3), (1, 200, 5, 3), (333, 256, 2, 1), (130, 64, 1, 4)])
-def test_resnet_tail_backward(R, C, nb, O):
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32", "auto"])
+@pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (64, 200, 5, 3), (1, 200, 5, 3), (333, 256, 2, 1), (130, 64, 1, 4),
+                                      (20000, 200, 5, 3)])
+def test_resnet_tail_backward(R, C, nb, O, impl, monkeypatch):
+    monkeypatch.setattr(ops, "TAIL_IMPL", impl)
     g = torch.Generator().manual_seed(R + C)
     r = lambda *s: torch.randn(*s, generator=g)
     H = 128
@@ -183,7 +204,10 @@ def test_resnet_tail_backward(R, C, nb, O):
     got.backward(go.float().to(DEV))
     for i, (d, c) in enumerate(zip(dev, cpu)):
         err = _rel_err(d.grad, c.grad)
-        assert err < 2e-4, (i, err)
+        # tensor-core path: every gradient of the tail passes through ReLU masks of recomputed activations (see
+        # _tc_grad_ok); d_wo / d_bo (i = 7, 8) do not
+        tol = 2e-4 if (impl == 1 or i >= 7) else 2e-2
+        assert err < tol, (i, err)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -217,7 +241,8 @@ def test_vattn_tc_stats_feed_backward(monkeypatch):
     want.sum().backward()
     got.sum().backward()
     for k in names:
-        assert _rel_err(dev[k].grad, cpu[k].grad) < 2e-4, k
+        ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad)
+        assert ok, (k, info)
 
 
 @pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (128, 200, 5, 3), (1, 200, 5, 3), (40000, 200, 5, 3), (515, 128, 2, 1),
