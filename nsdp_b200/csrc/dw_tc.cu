@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2);  // MMA commit + the column-sum warp
+      mbar_init(&empty[s], 5);  // MMA commit + the four column-sum warps
     }
     mbar_init(&acc_done, 1);
     mbar_fence_init();
@@ -103,29 +103,64 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       mma_commit(&acc_done);
     }
   } else if (has_work) {
-    if (warp == 2) {
-      // column sums of Y (bias gradients) straight from the staged slabs as they pass through shared memory:
-      // lane = column group of 8, 16 rows per k-step, hi + lo
+    {
+      // Column sums of Y straight from the staged slabs as they pass through shared memory. Lane = column group of 8;
+      // the four warps split the 16 rows of a k-step. All rows -> bias gradients (colsum); a periodic subset of rows
+      // (row % g_kr == g_kr - 1, g_kr a power of two) -> per-batch sums (gsum, the decoder's global-token rows).
+      const int w4 = warp - 2;
       float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const bool mine = job.colsum && lane * 8 < job.wy;
+      float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int gb = -1;   // batch the running gs[] belongs to
+      const bool mine = lane * 8 < job.wy;
+      const bool want_cs = job.colsum != nullptr, want_gs = job.gsum != nullptr;
+      const unsigned kr_mask = want_gs ? (unsigned)job.g_kr - 1u : 0u;
+      const int kr_shift = want_gs ? 31 - __clz(job.g_kr) : 0;
+      auto flush_gs = [&]() {
+        if (gb >= 0 && mine) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (lane * 8 + u < job.nv) atomicAdd(job.gsum + (size_t)gb * job.nv + lane * 8 + u, gs[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gs[u] = 0.f;
+      };
       uint32_t it = 0;
       for (long long t = t0; t < t1; ++t) {
         for (int ks = 0; ks < 8; ++ks, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph, p.err);
-          if (mine) {
+          if ((want_cs || want_gs) && mine) {
             const unsigned char *yh = smem + (size_t)s * stage_bytes + 2 * xs + (size_t)lane * 256;
             const unsigned char *yl = yh + ys;
-#pragma unroll 4
-            for (int rr = 0; rr < 16; ++rr) {
-              const uint4 h4 = *reinterpret_cast<const uint4 *>(yh + rr * 16);
-              const uint4 l4 = *reinterpret_cast<const uint4 *>(yl + rr * 16);
-              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            const unsigned row0 = (unsigned)(t * 128) + (unsigned)(ks * 16);   // row inside the segment (< 2^31)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                cs[2 * u] += __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
-                cs[2 * u + 1] += __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+            for (int q = 0; q < 4; ++q) {
+              const int rr = w4 + 4 * q;
+              const bool grow = want_gs && (((row0 + rr) & kr_mask) == kr_mask);
+              if (want_cs || grow) {
+                const uint4 h4 = *reinterpret_cast<const uint4 *>(yh + rr * 16);
+                const uint4 l4 = *reinterpret_cast<const uint4 *>(yl + rr * 16);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  v[2 * u] = __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+                  v[2 * u + 1] = __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                }
+                if (want_cs) {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) cs[u] += v[u];
+                }
+                if (grow) {
+                  const int b = (int)(((unsigned)job.g_centre0 + ((row0 + rr) >> kr_shift)) / (unsigned)job.g_M);
+                  if (b != gb) {
+                    flush_gs();
+                    gb = b;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) gs[u] += v[u];
+                }
               }
             }
           }
@@ -133,7 +168,8 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
           if (lane == 0) mbar_arrive(&empty[s]);
         }
       }
-      if (mine) {
+      if (want_gs) flush_gs();
+      if (want_cs && mine) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (lane * 8 + u < job.nv) atomicAdd(job.colsum + lane * 8 + u, cs[u]);

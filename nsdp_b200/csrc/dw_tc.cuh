@@ -12,6 +12,12 @@ struct Job {
   int wx, wy;              // padded widths (multiples of 16, <= 256)
   int mv, nv, ldo;         // valid extent / leading dimension of `out`
   float *colsum;           // optional [nv]: colsum[n] += sum_r Y[r][n]  (bias gradients), or nullptr
+  // optional per-batch sums over a periodic subset of the rows (the decoder's global-token rows):
+  //   gsum[b][n] += sum over rows r with r % g_kr == g_kr - 1 of Y[r][n],  b = (g_centre0 + row / g_kr) / g_M,
+  // where `row` counts from the first row of the job's first tile. nullptr disables it.
+  float *gsum;
+  int g_kr, g_M;
+  long long g_centre0;
 };
 
 }  // namespace dwtc

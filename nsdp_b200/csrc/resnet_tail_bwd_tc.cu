@@ -517,17 +517,17 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     dwtc::Job jobs[24];
     int nj = 0;
     // fc_out: d_wo_t[k][o] = x_n^T dout ; d_bo = colsum(dout)
-    jobs[nj++] = {stg.x[nb], stg.dout, g.d_wo_t, H, 16, H, a.O, a.O, g.d_bo};
+    jobs[nj++] = {stg.x[nb], stg.dout, g.d_wo_t, H, 16, H, a.O, a.O, g.d_bo, nullptr, 0, 0, 0};
     for (int i = 0; i < nb; ++i) {
       // fc_1[i]: d_w1_t[k][c] = y_i^T d net_{i+1} ; d_b1 = colsum
-      jobs[nj++] = {stg.y[i], stg.dn[i + 1], g.d_w1_t + (size_t)i * H * H, H, H, H, H, H, g.d_b1 + (size_t)i * H};
+      jobs[nj++] = {stg.y[i], stg.dn[i + 1], g.d_w1_t + (size_t)i * H * H, H, H, H, H, H, g.d_b1 + (size_t)i * H, nullptr, 0, 0, 0};
       // fc_0[i]: d_w0_t[k][c] = x_i^T dhh_i ; d_b0 = colsum
-      jobs[nj++] = {stg.x[i], stg.dhh[i], g.d_w0_t + (size_t)i * H * H, H, H, H, H, H, g.d_b0 + (size_t)i * H};
+      jobs[nj++] = {stg.x[i], stg.dhh[i], g.d_w0_t + (size_t)i * H * H, H, H, H, H, H, g.d_b0 + (size_t)i * H, nullptr, 0, 0, 0};
       // fc_c[i]: d_wc_t[kc][(i+1)H + c] = lat^T dn_i ; d_bc slice = colsum
-      jobs[nj++] = {stg.lat, stg.dn[i], g.d_wc_t + (size_t)(i + 1) * H, C::CP, H, a.C, H, wld, g.d_bc + (size_t)(i + 1) * H};
+      jobs[nj++] = {stg.lat, stg.dn[i], g.d_wc_t + (size_t)(i + 1) * H, C::CP, H, a.C, H, wld, g.d_bc + (size_t)(i + 1) * H, nullptr, 0, 0, 0};
     }
     // init_enc: d pre_0 = d net_0 = dn_0 as well
-    jobs[nj++] = {stg.lat, stg.dn[0], g.d_wc_t, C::CP, H, a.C, H, wld, g.d_bc};
+    jobs[nj++] = {stg.lat, stg.dn[0], g.d_wc_t, C::CP, H, a.C, H, wld, g.d_bc, nullptr, 0, 0, 0};
     rc = dw_tc_launch(jobs, nj, n, err, st);
     if (rc != NSDP_OK) return rc;
   }

@@ -29,10 +29,9 @@ struct BwdLayout {
   static constexpr int OFF_PC = OFF_WD0 + C::DP * 16;                 // float[DP]
   static constexpr int OFF_VC = OFF_PC + C::DP * 4;                   // float[DP]
   static constexpr int OFF_RELS = OFF_VC + C::DP * 4;                 // float4[128]  rel of every row of the tile
-  static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float4[128]  d rel accumulated over the parts
-  static constexpr int OFF_RGV = OFF_RELACC + 128 * 16;               // float[2][DP] per-tile reduction of d_gv
-  static constexpr int OFF_RGQ = OFF_RGV + 2 * C::DP * 4;             // float[2][DP]
-  static constexpr int OFF_BAR = OFF_RGQ + 2 * C::DP * 4;
+  static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float4[4][128]  d rel, one slot per column part
+  static constexpr int OFF_RGV = OFF_RELACC + 4 * 128 * 16;           // (unused, kept for layout stability)
+  static constexpr int OFF_BAR = OFF_RGV;
   static constexpr int SMEM = OFF_BAR + 256;
   // fp32 scratch [col][128] aliasing the A buffer (exactly 2 * A_HALF bytes for D == DP); element (col, row) sits at
   // col*128 + ((row + col) & 127): the rotation keeps both the row-wise writes and the column-wise reads conflict-free
@@ -127,8 +126,6 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   float *vcs = reinterpret_cast<float *>(smem + L::OFF_VC);
   float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
   float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
-  float *rgv = reinterpret_cast<float *>(smem + L::OFF_RGV);
-  float *rgq = reinterpret_cast<float *>(smem + L::OFF_RGQ);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
   uint64_t *full = bars, *empty = bars + C::STAGES, *a_ready = bars + 2 * C::STAGES, *acc_done = a_ready + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
@@ -149,8 +146,6 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
     wd0s[kk] = w;
     pcs[kk] = p;
     vcs[kk] = v;
-    rgv[kk] = rgv[C::DP + kk] = 0.f;
-    rgq[kk] = rgq[C::DP + kk] = 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -260,12 +255,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       const RowInfo ri = row_info<C>(a, tile, r, krows);
       const bool row_on = ri.c >= 0;
       const bool is_glob = row_on && ri.n < 0;
-      const int b0 = (int)((tile * C::CENTRES) / a.M);                 // batch of the tile's first centre
-      const int bslot = is_glob ? (-ri.n - 1) - b0 : 0;                 // 0 or 1 (tiles span at most 2 shapes if M >= 16)
-      if (part == 0) {
-        rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
-        *reinterpret_cast<float4 *>(relacc + r * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      if (part == 0) rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
       float R[C::MAXCH][8];
       unsigned long long gmaskbits = 0ull;
       // ---- H operand (+ staged for d_wpt / d_wd2t) ---------------------------------------------------------
@@ -385,18 +375,8 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
               ds[j + u] = w * gos[u];
               da[j + u] = ds[j + u] * (s - os[u]);
             }
-            if (on) {
-              if (!is_glob) {
-                if (g.d_vp) red_add_v4(g.d_vp + (size_t)ri.n * D + col, ds[j], ds[j + 1], ds[j + 2], ds[j + 3]);
-              } else if (g.d_gv) {
-                if (bslot < 2) {
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) atomicAdd(&rgv[bslot * C::DP + col + u], ds[j + u]);
-                } else {
-                  red_add_v4(g.d_gv + (size_t)(-ri.n - 1) * D + col, ds[j], ds[j + 1], ds[j + 2], ds[j + 3]);
-                }
-              }
-            }
+            if (on && !is_glob && g.d_vp)
+              red_add_v4(g.d_vp + (size_t)ri.n * D + col, ds[j], ds[j + 1], ds[j + 2], ds[j + 3]);
           }
           write_operand<C>(A_hi, A_lo, stg.da + st_off, r, k0, da);
           write_operand<C>(nullptr, nullptr, stg.ds + st_off, r, k0, ds);
@@ -424,18 +404,9 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
             const int col = k0 + j;
-            if (row_on && col < D) {
-              if (!is_glob) {
-                if (g.d_kp) red_add_v4(g.d_kp + (size_t)ri.n * D + col, -dg[j], -dg[j + 1], -dg[j + 2], -dg[j + 3]);
-                if (g.d_qp) red_add_v4(g.d_qp + (size_t)ri.c * D + col, dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
-              } else if (g.d_gq) {
-                if (bslot < 2) {
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) atomicAdd(&rgq[bslot * C::DP + col + u], dg[j + u]);
-                } else {
-                  red_add_v4(g.d_gq + (size_t)(-ri.n - 1) * D + col, dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
-                }
-              }
+            if (row_on && col < D && !is_glob) {
+              if (g.d_kp) red_add_v4(g.d_kp + (size_t)ri.n * D + col, -dg[j], -dg[j + 1], -dg[j + 2], -dg[j + 3]);
+              if (g.d_qp) red_add_v4(g.d_qp + (size_t)ri.c * D + col, dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
             }
           }
           write_operand<C>(nullptr, nullptr, stg.dgp + st_off, r, k0, dg);
@@ -471,11 +442,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             }
           }
         }
-        if (ri.flag != 0.f) {
-          atomicAdd(&relacc[r * 4 + 0], sx);
-          atomicAdd(&relacc[r * 4 + 1], sy);
-          atomicAdd(&relacc[r * 4 + 2], sz);
-        }
+        *reinterpret_cast<float4 *>(relacc + (part * 128 + r) * 4) = make_float4(sx, sy, sz, 0.f);
       }
       tc_fence_before();
       asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -488,23 +455,15 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           const float4 rl = rels[rr];
           cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
         }
-        // per-tile flush of the global-row reductions
-        if (a.has_global) {
-          for (int sl = 0; sl < 2; ++sl) {
-            const int bb = b0 + sl;
-            if (bb < a.B) {
-              const float v = rgv[sl * C::DP + wtid], qv = rgq[sl * C::DP + wtid];
-              if (g.d_gv && v != 0.f) atomicAdd(g.d_gv + (size_t)bb * D + wtid, v);
-              if (g.d_gq && qv != 0.f) atomicAdd(g.d_gq + (size_t)bb * D + wtid, qv);
-            }
-            rgv[sl * C::DP + wtid] = 0.f;
-            rgq[sl * C::DP + wtid] = 0.f;
-          }
-        }
       }
       // row owners: d_xyz
       if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {
-        const float sx = relacc[r * 4 + 0], sy = relacc[r * 4 + 1], sz = relacc[r * 4 + 2];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < C::NPART; ++pp) {
+          const float4 t = *reinterpret_cast<const float4 *>(relacc + (pp * 128 + r) * 4);
+          sx += t.x; sy += t.y; sz += t.z;
+        }
         if (g.d_xyz_c) {
           float *dst = g.d_xyz_c + (size_t)ri.c * 3;
           atomicAdd(dst, a.sign * sx); atomicAdd(dst + 1, a.sign * sy); atomicAdd(dst + 2, a.sign * sz);
@@ -588,9 +547,12 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
     rc = check_launch();
     if (rc != NSDP_OK) return rc;
     dwtc::Job jobs[3] = {
-        {stg.g, stg.da, g.d_wg2t, C::DP, C::DP, a.D, a.D, a.D, nullptr},
-        {stg.h, stg.dgp, g.d_wpt, C::DP, C::DP, a.D, a.D, a.D, nullptr},
-        {stg.h, stg.ds, g.d_wd2t, C::DP, C::DP, a.D, a.D, a.D, nullptr},
+        {stg.g, stg.da, g.d_wg2t, C::DP, C::DP, a.D, a.D, a.D, nullptr, nullptr, 0, 0, 0},
+        // the global-token rows (row % KR == KR-1) of dGP / dS sum up to d_gq / d_gv per shape
+        {stg.h, stg.dgp, g.d_wpt, C::DP, C::DP, a.D, a.D, a.D, nullptr, a.has_global ? g.d_gq : nullptr, C::KR, a.M,
+         t0 * C::CENTRES},
+        {stg.h, stg.ds, g.d_wd2t, C::DP, C::DP, a.D, a.D, a.D, nullptr, a.has_global ? g.d_gv : nullptr, C::KR, a.M,
+         t0 * C::CENTRES},
     };
     rc = dw_tc_launch(jobs, 3, n, err, st);
     if (rc != NSDP_OK) return rc;

@@ -1,0 +1,20 @@
+"""Decoder cross-attention + tail, forward and backward, at C2 size; target for ncu captures of the backward kernels."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nsdp_b200 import synth
+from nsdp_b200.model import build_model
+dev = "cuda:0"
+B, N, Q = int(os.environ.get("B", 8)), 4096, int(os.environ.get("Q", 50000))
+model, *_ = build_model(synth.make_config("forward"), device=dev)
+schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+model.load_state_dict(synth.named_state_dict(schema, seed=0)); model.train()
+batch = {k: v.to(dev) for k, v in synth.forward_batch(B, N, Q, seed=1).items()}
+with torch.no_grad():
+    enc = model.encode(batch["surface_samples_inputs"])
+enc = {k: v.detach().requires_grad_(k != "anchors") for k, v in enc.items()}
+for it in range(int(os.environ.get("REPS", 2))):
+    out = model.decode(batch["space_samples_src"], enc)
+    out.square().mean().backward()
+torch.cuda.synchronize()
+print("ok")
