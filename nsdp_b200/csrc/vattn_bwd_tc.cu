@@ -30,9 +30,9 @@ struct BwdLayout {
   static constexpr int OFF_VC = OFF_PC + C::DP * 4;                   // float[DP]
   static constexpr int OFF_RELS = OFF_VC + C::DP * 4;                 // float4[128]  rel of every row of the tile
   static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float4[4][128]  d rel, one slot per column part
-  static constexpr int OFF_RGV = OFF_RELACC + 4 * 128 * 16;           // (unused, kept for layout stability)
+  static constexpr int OFF_RGV = OFF_RELACC + C::NPART * 128 * 16;
   static constexpr int OFF_BAR = OFF_RGV;
-  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int SMEM = OFF_BAR + 128;
   // fp32 scratch [col][128] aliasing the A buffer (exactly 2 * A_HALF bytes for D == DP); element (col, row) sits at
   // col*128 + ((row + col) & 127): the rotation keeps both the row-wise writes and the column-wise reads conflict-free
   static constexpr int SCR_LD = 128;
@@ -108,6 +108,19 @@ __device__ __forceinline__ void write_operand(unsigned char *A_hi, unsigned char
     *reinterpret_cast<uint4 *>(p) = hi;
     *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
   }
+}
+
+// Re-loads one staged 8-column chunk (written earlier by THIS thread) and stores it as the A operand: the operand
+// tiles ds / dgp are needed again one GEMM later, and keeping them in registers across the wait costs 56 registers.
+template <class C>
+__device__ __forceinline__ void staged_to_operand(unsigned char *A_hi, unsigned char *A_lo, const unsigned char *stage_tile,
+                                                  int r, int k0) {
+  const unsigned char *p = stage_tile + (size_t)(r >> 4) * (2 * C::DP * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
+  const uint4 hi = *reinterpret_cast<const uint4 *>(p);
+  const uint4 lo = *reinterpret_cast<const uint4 *>(p + C::DP * 32);
+  const uint32_t off = canon_off(128, r, k0);
+  *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+  *reinterpret_cast<uint4 *>(A_lo + off) = lo;
 }
 
 template <class C>
@@ -380,8 +393,6 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           }
           write_operand<C>(A_hi, A_lo, stg.da + st_off, r, k0, da);
           write_operand<C>(nullptr, nullptr, stg.ds + st_off, r, k0, ds);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) R[q][j] = ds[j];
         }
       }
       publish();
@@ -389,7 +400,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       wait_acc();
 #pragma unroll
       for (int q = 0; q < C::MAXCH; ++q) {
-        if (q < nch) write_operand<C>(A_hi, A_lo, nullptr, r, (ch0 + q) * 8, R[q]);
+        if (q < nch) staged_to_operand<C>(A_hi, A_lo, stg.ds + st_off, r, (ch0 + q) * 8);
       }
       publish();
       // ---- dgp = dg * [g > 0] (reads acc0 while GEMM4a fills acc1); scatter d_kp / d_qp / d_gq -------------------------------
@@ -410,15 +421,13 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             }
           }
           write_operand<C>(nullptr, nullptr, stg.dgp + st_off, r, k0, dg);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) R[q][j] = dg[j];
         }
       }
       // ---- GEMM4a done: A is free -> operand dgp (GEMM4b) ----------------------------------------------------------------------
       wait_acc();
 #pragma unroll
       for (int q = 0; q < C::MAXCH; ++q) {
-        if (q < nch) write_operand<C>(A_hi, A_lo, nullptr, r, (ch0 + q) * 8, R[q]);
+        if (q < nch) staged_to_operand<C>(A_hi, A_lo, stg.dgp + st_off, r, (ch0 + q) * 8);
       }
       publish();
       // ---- dpre = dh * [h > 0]; d rel; dpre -> fp32 scratch (aliases A, free once GEMM4b is done) ------------------------------
@@ -445,7 +454,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
         *reinterpret_cast<float4 *>(relacc + (part * 128 + r) * 4) = make_float4(sx, sy, sz, 0.f);
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
       // column owners: d_wd0 / d_bd0 partial sums over the 128 rows of the tile
       if (wtid < D) {
         const float *colp = scratch + (size_t)wtid * L::SCR_LD;
@@ -473,7 +482,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           atomicAdd(dst, -a.sign * sx); atomicAdd(dst + 1, -a.sign * sy); atomicAdd(dst + 2, -a.sign * sz);
         }
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
     }
     if (wtid < D) {
       if (g.d_wd0) {
@@ -575,12 +584,17 @@ static int pick_bwd(const nsdp_vattn_args &a) {
 
 }  // namespace vtc
 
+#ifndef NSDP_BWD_NPART
+#define NSDP_BWD_NPART 4
+#endif
+constexpr int BWD_NPART = NSDP_BWD_NPART;  // worker warps per TMEM lane quarter in the backward chain kernel
+
 size_t vattn_bwd_tc_workspace_bytes(const nsdp_vattn_args *a) {
   switch (vtc::pick_bwd(*a)) {
-    case 1: return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8>>(*a);
-    case 2: return vtc::bwd_workspace_bytes<vtc::TcCfg<128, 16>>(*a);
-    case 3: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 16>>(*a);
-    case 4: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 128>>(*a);
+    case 1: return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8, BWD_NPART>>(*a);
+    case 2: return vtc::bwd_workspace_bytes<vtc::TcCfg<128, 16, BWD_NPART>>(*a);
+    case 3: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 16, BWD_NPART>>(*a);
+    case 4: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 128, BWD_NPART>>(*a);
     default: return 0;
   }
 }
@@ -589,10 +603,10 @@ int vattn_bwd_tc_dispatch(const nsdp_vattn_args *a, const float *out, const floa
                           const nsdp_vattn_grads *g, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled) {
   *handled = true;
   switch (vtc::pick_bwd(*a)) {
-    case 1: return vtc::launch_bwd<vtc::TcCfg<208, 8>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
-    case 2: return vtc::launch_bwd<vtc::TcCfg<128, 16>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
-    case 3: return vtc::launch_bwd<vtc::TcCfg<256, 16>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
-    case 4: return vtc::launch_bwd<vtc::TcCfg<256, 128>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 1: return vtc::launch_bwd<vtc::TcCfg<208, 8, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 2: return vtc::launch_bwd<vtc::TcCfg<128, 16, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 3: return vtc::launch_bwd<vtc::TcCfg<256, 16, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 4: return vtc::launch_bwd<vtc::TcCfg<256, 128, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
     default: *handled = false; return NSDP_OK;
   }
 }

@@ -10,7 +10,7 @@ namespace vtc {
 
 using namespace umma;
 
-template <int DP_, int KR_>
+template <int DP_, int KR_, int NPART_ = 4>
 struct TcCfg {
   static constexpr int DP = DP_;                 // padded channel count: K and N of every GEMM
   static constexpr int KR = KR_;                 // rows per centre inside a tile (power of two, 8..32)
@@ -19,7 +19,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 4 * SLAB;   // GEMM1 stage: W' hi, W' lo, Wd2 hi, Wd2 lo (GEMM2 uses half)
   static constexpr int STAGES = DP > 208 ? 2 : 4;
   static constexpr int A_HALF = 128 * DP * 2;    // bytes of the hi (or lo) A operand
-  static constexpr int NPART = 4;                // worker warps per TMEM lane quarter (they split the columns)
+  static constexpr int NPART = NPART_;           // worker warps per TMEM lane quarter (they split the columns)
   static constexpr int WORKER_WARPS = 4 * NPART;
   static constexpr int THREADS = (2 + WORKER_WARPS) * 32;
   static constexpr int CHUNKS = DP / 8;          // 8-column chunks per row
