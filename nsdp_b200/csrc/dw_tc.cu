@@ -10,6 +10,8 @@
 //     byte(r, c) = (r / 16) * (2 * W * 32) + [hi: 0 | lo: W * 32] + (c / 8) * 256 + (r % 16) * 16 + (c % 8) * 2
 // i.e. per k-step (16 rows) one contiguous [hi slab][lo slab] pair; inside a slab the 8 contiguous elements run
 // along the OUTPUT dimension, so the slab is consumed directly as an MN-major operand (LBO = 128, SBO = 256).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dw_tc.cuh"
 #include "umma.cuh"
@@ -28,6 +30,7 @@ struct Params {
   int njobs;
   int splits;              // CTAs per job
   long long tiles;         // row tiles per job (same for all jobs of a launch)
+  int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
   int *err;
 };
 
@@ -40,7 +43,9 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   const Job job = p.jobs[jid];
   const long long t0 = p.tiles * split / p.splits, t1 = p.tiles * (split + 1) / p.splits;
   const uint32_t xs = (uint32_t)job.wx * 32, ys = (uint32_t)job.wy * 32;  // slab bytes
-  const uint32_t stage_bytes = 2 * xs + 2 * ys;
+  const bool x_lo = p.terms >= 2, y_lo = p.terms >= 3;   // which lo slabs are streamed at all
+  const uint32_t xb = x_lo ? 2 * xs : xs, yb = y_lo ? 2 * ys : ys;
+  const uint32_t stage_bytes = xb + yb;
   const int mtiles = job.wx > 128 ? 2 : 1;
 
   if (tid == 0) {
@@ -70,8 +75,8 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
           mbar_wait(&empty[s], ph ^ 1, p.err);
           mbar_arrive_expect_tx(&full[s], stage_bytes);
           unsigned char *dst = smem + (size_t)s * stage_bytes;
-          bulk_g2s(dst, xt + (size_t)ks * 2 * xs, 2 * xs, &full[s]);
-          bulk_g2s(dst + 2 * xs, yt + (size_t)ks * 2 * ys, 2 * ys, &full[s]);
+          bulk_g2s(dst, xt + (size_t)ks * 2 * xs, xb, &full[s]);
+          bulk_g2s(dst + xb, yt + (size_t)ks * 2 * ys, yb, &full[s]);
         }
       }
     }
@@ -87,14 +92,14 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
           mbar_wait(&full[s], ph, p.err);
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t yh = smem_desc(sb + 2 * xs, 128, 256), yl = smem_desc(sb + 2 * xs + ys, 128, 256);
+          const uint64_t yh = smem_desc(sb + xb, 128, 256), yl = smem_desc(sb + xb + ys, 128, 256);
           for (int j = 0; j < mtiles; ++j) {
             // M-tile j = output rows [128j, 128j+128) = column groups 16j.. of the X slab (4096 bytes further)
             const uint64_t xh = smem_desc(sb + j * 4096, 128, 256), xl = smem_desc(sb + xs + j * 4096, 128, 256);
             const uint32_t d = tmem_base + j * 256;
             mma_bf16(d, xh, yh, idesc, !first);
-            mma_bf16(d, xl, yh, idesc, true);
-            mma_bf16(d, xh, yl, idesc, true);
+            if (x_lo) mma_bf16(d, xl, yh, idesc, true);
+            if (y_lo) mma_bf16(d, xh, yl, idesc, true);
           }
           first = false;
           mma_commit(&empty[s]);
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph, p.err);
           if ((want_cs || want_gs) && mine) {
-            const unsigned char *yh = smem + (size_t)s * stage_bytes + 2 * xs + (size_t)lane * 256;
+            const unsigned char *yh = smem + (size_t)s * stage_bytes + xb + (size_t)lane * 256;
             const unsigned char *yl = yh + ys;
             const unsigned row0 = (unsigned)(t * 128) + (unsigned)(ks * 16);   // row inside the segment (< 2^31)
 #pragma unroll
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
               const bool grow = want_gs && (((row0 + rr) & kr_mask) == kr_mask);
               if (want_cs || grow) {
                 const uint4 h4 = *reinterpret_cast<const uint4 *>(yh + rr * 16);
-                const uint4 l4 = *reinterpret_cast<const uint4 *>(yl + rr * 16);
+                const uint4 l4 = y_lo ? *reinterpret_cast<const uint4 *>(yl + rr * 16) : make_uint4(0u, 0u, 0u, 0u);
                 const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
                 float v[8];
 #pragma unroll
@@ -201,6 +206,16 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
 
 }  // namespace dwtc
 
+// Precision of the weight-gradient reduction (NSDP_DW_TERMS = 1 | 2 | 3, default 3 = fp32-grade bf16x3).
+static int dw_terms() {
+  static const int t = [] {
+    const char *e = getenv("NSDP_DW_TERMS");
+    const int v = e ? atoi(e) : 3;
+    return v < 1 || v > 3 ? 3 : v;
+  }();
+  return t;
+}
+
 // Launches the reduction for `njobs` jobs that all span `tiles` row tiles.
 int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cudaStream_t st) {
   using namespace dwtc;
@@ -218,6 +233,7 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   if (splits > tiles) splits = (int)tiles;
   p.splits = splits;
   p.tiles = tiles;
+  p.terms = dw_terms();
   p.err = err;
   const size_t smem = (size_t)STAGES * 64 * maxw + 4096;  // stage = 2*32*(wx+wy); + slack for the M-tile-1 overrun
   cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,6 +15,8 @@
 // hi/lo in the k-step-major layout documented in dw_tc.cu and reduced by dw_tc_kernel:
 //     d_wg2t += G^T dA,   d_wpt += H^T dGP,   d_wd2t += H^T dS.
 // The op processes the rows in segments so that the staging workspace stays bounded.
+#include <stdlib.h>
+
 #include "dw_tc.cuh"
 #include "vattn_tc_common.cuh"
 
@@ -511,7 +513,16 @@ __global__ void finalize_scatter_kernel(const float *__restrict__ tmp, float *__
   if (colsum) atomicAdd(colsum + c, sign * s);
 }
 
-constexpr long long kSegmentTiles = 2048;  // staging workspace = 5 tensors x 2048 tiles x 104 KB = 1.06 GB
+// staging workspace = 5 tensors x 2048 tiles x 104 KB = 1.06 GB (NSDP_VATTN_SEG overrides the segment length)
+static long long segment_tiles() {
+  static const long long v = [] {
+    const char *e = getenv("NSDP_VATTN_SEG");
+    const long long t = e ? atoll(e) : 2048;
+    return t < 1 || t > 2048 ? 2048ll : t;
+  }();
+  return v;
+}
+#define kSegmentTiles segment_tiles()
 
 template <class C>
 static size_t bwd_workspace_bytes(const nsdp_vattn_args &a) {

@@ -13,8 +13,11 @@ batch = {k: v.to(dev) for k, v in synth.forward_batch(B, N, Q, seed=1).items()}
 with torch.no_grad():
     enc = model.encode(batch["surface_samples_inputs"])
 enc = {k: v.detach().requires_grad_(k != "anchors") for k, v in enc.items()}
-for it in range(int(os.environ.get("REPS", 2))):
+reps = int(os.environ.get("REPS", 2))
+for it in range(reps):
+    if it == reps - 1:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()
     out = model.decode(batch["space_samples_src"], enc)
     out.square().mean().backward()
-torch.cuda.synchronize()
+torch.cuda.synchronize(); torch.cuda.profiler.stop()
 print("ok")
