@@ -21,7 +21,7 @@ namespace dwtc {
 
 using namespace umma;
 
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;   // ring depth is chosen per launch: as many stages as fit in shared memory (HBM latency)
 constexpr int THREADS = 6 * 32;  // warp 0 producer, warp 1 MMA, warps 2..5 flush
 constexpr int MAX_JOBS = 24;
 
@@ -30,13 +30,15 @@ struct Params {
   int njobs;
   int splits;              // CTAs per job
   long long tiles;         // row tiles per job (same for all jobs of a launch)
+  int stages;              // ring depth (<= MAX_STAGES)
   int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
   int *err;
 };
 
 __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_done;
+  __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_done;
+  const int STAGES = p.stages;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jid = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
@@ -235,7 +237,15 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   p.tiles = tiles;
   p.terms = dw_terms();
   p.err = err;
-  const size_t smem = (size_t)STAGES * 64 * maxw + 4096;  // stage = 2*32*(wx+wy); + slack for the M-tile-1 overrun
+  // stage = 2*32*(wx+wy) bytes; + slack for the M-tile-1 overrun. The ring is as deep as shared memory allows: the
+  // operand tiles stream from HBM (several microseconds of latency under load), 4 stages left the SMs waiting
+  int stages = (int)((227 * 1024 - 4096 - 1024) / ((size_t)64 * maxw));
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return NSDP_ERR_UNSUPPORTED;
+  static const int forced = [] { const char *e = getenv("NSDP_DW_STAGES"); return e ? atoi(e) : 0; }();
+  if (forced >= 2 && forced < stages) stages = forced;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * 64 * maxw + 4096;
   cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
   dw_tc_kernel<<<njobs * splits, THREADS, smem, st>>>(p);

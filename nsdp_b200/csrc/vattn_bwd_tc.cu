@@ -26,15 +26,16 @@ namespace vtc {
 template <class C>
 struct BwdLayout {
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_STAGE = OFF_A + 2 * C::A_HALF;
-  static constexpr int OFF_WD0 = OFF_STAGE + C::STAGES * C::STAGE_BYTES;  // float4[DP]
+  static constexpr int OFF_E = OFF_A + 2 * C::A_HALF;
+  static constexpr int OFF_STAGE = OFF_E + C::E_BYTES;
+  static constexpr int OFF_WD0 = OFF_STAGE + C::SLOTS * C::SLOT_BYTES;    // float4[DP]
   static constexpr int OFF_PC = OFF_WD0 + C::DP * 16;                 // float[DP]
   static constexpr int OFF_VC = OFF_PC + C::DP * 4;                   // float[DP]
   static constexpr int OFF_RELS = OFF_VC + C::DP * 4;                 // float4[128]  rel of every row of the tile
-  static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float4[4][128]  d rel, one slot per column part
-  static constexpr int OFF_RGV = OFF_RELACC + C::NPART * 128 * 16;
+  static constexpr int OFF_RELACC = OFF_RELS + 128 * 16;              // float[NPART][3][128]  d rel, one slot per column part
+  static constexpr int OFF_RGV = OFF_RELACC + C::NPART * 3 * 128 * 4;
   static constexpr int OFF_BAR = OFF_RGV;
-  static constexpr int SMEM = OFF_BAR + 128;
+  static constexpr int SMEM = OFF_BAR + 256;
   // fp32 scratch [col][128] aliasing the A buffer (exactly 2 * A_HALF bytes for D == DP); element (col, row) sits at
   // col*128 + ((row + col) & 127): the rotation keeps both the row-wise writes and the column-wise reads conflict-free
   static constexpr int SCR_LD = 128;
@@ -149,7 +150,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
   float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + C::STAGES, *a_ready = bars + 2 * C::STAGES, *acc_done = a_ready + 1;
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -170,7 +171,7 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
     vcs[kk] = v;
   }
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < C::SLOTS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -183,26 +184,19 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t HALF = C::STAGE_BYTES / 2;
-  // byte offsets of the five weight regions inside `packed`
-  constexpr size_t REG1 = 0, REG2 = (size_t)C::KSTEPS * 4 * C::SLAB, REG3 = REG2 + (size_t)C::KSTEPS * 2 * C::SLAB,
-                   REG4 = REG3 + (size_t)C::KSTEPS * 2 * C::SLAB, REG5 = REG4 + (size_t)C::KSTEPS * 2 * C::SLAB;
-
   if (warp == 0) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      const size_t reg[5] = {REG1, REG2, REG3, REG4, REG5};
+      uint32_t it = 0;   // slot counter (one slot = one matrix k-step: hi slab + lo slab)
       for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        for (int gi = 0; gi < 5; ++gi) {
-          const uint32_t bytes = gi == 0 ? C::STAGE_BYTES : HALF;
-          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (it / C::STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1, err);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, packed + reg[gi] + (size_t)ks * bytes, bytes, &full[s]);
-          }
+        // the packed image is consumed front to back: GEMM1 takes 2 slots per k-step, GEMM2..4b one
+        const unsigned char *src = packed;
+        for (int j = 0; j < 6 * C::KSTEPS; ++j, ++it, src += C::SLOT_BYTES) {
+          const int s = it % C::SLOTS;
+          const uint32_t ph = (it / C::SLOTS) & 1;
+          mbar_wait(&empty[s], ph ^ 1, err);
+          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
         }
       }
     }
@@ -221,26 +215,23 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           // destination accumulator / accumulate-into flags of the five GEMMs
           const uint32_t dcol = (gi == 3 || gi == 4) ? C::ACC1_COL : 0;
           const bool keep = gi == 4;  // GEMM4b adds to GEMM4a's result
-          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (it / C::STAGES) & 1;
-            mbar_wait(&full[s], ph, err);
-            tc_fence_after();
-            const uint32_t sb = smem_u32(stage0 + (size_t)s * C::STAGE_BYTES);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
             const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
             const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
-            const bool acc = keep || ks > 0;
-            const uint64_t b0h = smem_desc(sb, lbo_b, 128), b0l = smem_desc(sb + C::SLAB, lbo_b, 128);
-            mma_bf16(tmem_base + dcol, ah, b0h, idesc, acc);
-            mma_bf16(tmem_base + dcol, al, b0h, idesc, true);
-            mma_bf16(tmem_base + dcol, ah, b0l, idesc, true);
-            if (gi == 0) {
-              const uint64_t b1h = smem_desc(sb + 2 * C::SLAB, lbo_b, 128), b1l = smem_desc(sb + 3 * C::SLAB, lbo_b, 128);
-              mma_bf16(tmem_base + C::ACC1_COL, ah, b1h, idesc, ks > 0);
-              mma_bf16(tmem_base + C::ACC1_COL, al, b1h, idesc, true);
-              mma_bf16(tmem_base + C::ACC1_COL, ah, b1l, idesc, true);
+            for (int m = 0; m < (gi == 0 ? 2 : 1); ++m, ++it) {   // GEMM1: W' -> acc0, then Wd2 -> acc1
+              const int s = it % C::SLOTS;
+              const uint32_t ph = (it / C::SLOTS) & 1;
+              mbar_wait(&full[s], ph, err);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
+              const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : dcol);
+              const bool acc = keep || ks > 0;
+              mma_bf16(d, ah, bh, idesc, acc);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bl, idesc, true);
+              mma_commit(&empty[s]);
             }
-            mma_commit(&empty[s]);
           }
           mma_commit(acc_done);
         }
@@ -454,7 +445,9 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             }
           }
         }
-        *reinterpret_cast<float4 *>(relacc + (part * 128 + r) * 4) = make_float4(sx, sy, sz, 0.f);
+        relacc[(part * 3 + 0) * 128 + r] = sx;
+        relacc[(part * 3 + 1) * 128 + r] = sy;
+        relacc[(part * 3 + 2) * 128 + r] = sz;
       }
       tc_fence_before();
       asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
@@ -473,8 +466,9 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
         for (int pp = 0; pp < C::NPART; ++pp) {
-          const float4 t = *reinterpret_cast<const float4 *>(relacc + (pp * 128 + r) * 4);
-          sx += t.x; sy += t.y; sz += t.z;
+          sx += relacc[(pp * 3 + 0) * 128 + r];
+          sy += relacc[(pp * 3 + 1) * 128 + r];
+          sz += relacc[(pp * 3 + 2) * 128 + r];
         }
         if (g.d_xyz_c) {
           float *dst = g.d_xyz_c + (size_t)ri.c * 3;

@@ -20,6 +20,7 @@
 // Precision: fp32 operands are split into bf16 hi + lo and every product is hi*hi + lo*hi + hi*lo accumulated in
 // fp32 (umma.cuh); the result matches the fp32 CUDA-core kernel to ~1e-6 relative.
 #include <math.h>
+#include <stdlib.h>
 
 #include "vattn_tc_common.cuh"
 
@@ -76,9 +77,9 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   float *pcs = reinterpret_cast<float *>(smem + C::OFF_PC);
   float *vcs = reinterpret_cast<float *>(smem + C::OFF_VC);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-  uint64_t *full = bars;                    // [STAGES]
-  uint64_t *empty = bars + C::STAGES;       // [STAGES]
-  uint64_t *a_ready = bars + 2 * C::STAGES; // workers -> MMA (count = worker warps)
+  uint64_t *full = bars;                    // [SLOTS]
+  uint64_t *empty = bars + C::SLOTS;        // [SLOTS]
+  uint64_t *a_ready = bars + 2 * C::SLOTS;  // workers -> MMA (count = worker warps)
   uint64_t *acc_done = a_ready + 1;         // MMA -> workers (tcgen05.commit)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
 
@@ -99,7 +100,7 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
     vcs[kk] = v;
   }
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < C::SLOTS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -116,18 +117,16 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   if (warp == 0) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0;   // slot counter
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t bytes = g == 0 ? C::STAGE_BYTES : C::STAGE_BYTES / 2;
-          const unsigned char *src = packed + (g == 0 ? 0 : (size_t)C::KSTEPS * C::STAGE_BYTES);
-          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (it / C::STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1, err);  // first round passes immediately (fresh barrier, parity trick)
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, src + (size_t)ks * bytes, bytes, &full[s]);
-          }
+        // the packed image is consumed front to back: 2 slots per k-step of GEMM1, then 1 slot per k-step of GEMM2
+        const unsigned char *src = packed;
+        for (int j = 0; j < 3 * C::KSTEPS; ++j, ++it, src += C::SLOT_BYTES) {
+          const int s = it % C::SLOTS;
+          const uint32_t ph = (it / C::SLOTS) & 1;
+          mbar_wait(&empty[s], ph ^ 1, err);  // first round passes immediately (fresh barrier, parity trick)
+          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
         }
       }
     }
@@ -143,27 +142,24 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           mbar_wait(a_ready, ready_phase, err);
           ready_phase ^= 1;
           tc_fence_after();
-          for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (it / C::STAGES) & 1;
-            mbar_wait(&full[s], ph, err);
-            tc_fence_after();
-            const uint32_t sb = smem_u32(stage0 + (size_t)s * C::STAGE_BYTES);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
             const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
             const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
             const bool acc = ks > 0;
-            // matrix 0 (W' in GEMM1, Wg2 in GEMM2) -> acc0
-            const uint64_t b0h = smem_desc(sb, lbo_b, 128), b0l = smem_desc(sb + C::SLAB, lbo_b, 128);
-            mma_bf16(tmem_base, ah, b0h, idesc, acc);
-            mma_bf16(tmem_base, al, b0h, idesc, true);
-            mma_bf16(tmem_base, ah, b0l, idesc, true);
-            if (g == 0) {  // matrix 1 (Wd2) -> acc1
-              const uint64_t b1h = smem_desc(sb + 2 * C::SLAB, lbo_b, 128), b1l = smem_desc(sb + 3 * C::SLAB, lbo_b, 128);
-              mma_bf16(tmem_base + C::ACC1_COL, ah, b1h, idesc, acc);
-              mma_bf16(tmem_base + C::ACC1_COL, al, b1h, idesc, true);
-              mma_bf16(tmem_base + C::ACC1_COL, ah, b1l, idesc, true);
+            // GEMM1: slot 0 = W' -> acc0, slot 1 = Wd2 -> acc1 ; GEMM2: one slot, Wg2 -> acc0
+            for (int m = 0; m < (g == 0 ? 2 : 1); ++m, ++it) {
+              const int s = it % C::SLOTS;
+              const uint32_t ph = (it / C::SLOTS) & 1;
+              mbar_wait(&full[s], ph, err);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
+              const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+              mma_bf16(d, ah, bh, idesc, acc);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bl, idesc, true);
+              mma_commit(&empty[s]);
             }
-            mma_commit(&empty[s]);
           }
           mma_commit(acc_done);
         }
@@ -416,6 +412,352 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+
+// =====================================================================================================================
+// OH variant (decoder cross-attention, C::OH): no per-row gathers. GEMM1 is extended by E_KSTEPS k-steps over the
+// one-hot operand E (row r has a single 1 in column j_r = neighbour index, or N for the global-token row):
+//     acc0 = H * W'^T + E * T1_b,   T1_b[j] = -kp[b][j] (j < N),  T1_b[N] = gq[b] - pc      ->  G = relu(acc0 + pc)
+//     acc1 = H * Wd2^T + E * T2_b,  T2_b[j] =  vp[b][j] (j < N),  T2_b[N] = gv[b] - vc      ->  s = acc1 + vc
+// (H = 0 on the global row, so that row sees exactly gq / gv.) Tiles never straddle shapes (row_info_pb), the tables of
+// shape b are pre-packed like the weights and stream through the same slot ring. E is exact in bf16: 2 MMAs per k-step.
+// =====================================================================================================================
+template <class C>
+constexpr size_t table_bytes_per_shape() {
+  return (size_t)C::E_KSTEPS * 2 * C::SLOT_BYTES;   // per k-step: [T1 hi][T1 lo][T2 hi][T2 lo]
+}
+
+template <class C>
+__global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__restrict__ out) {
+  // one thread per (shape b, table m, column n, anchor pair k)
+  const int per = C::DP * (C::E_COLS / 2);
+  const long long total = (long long)a.B * 2 * per;
+  const int D = a.D, N = a.N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / (2 * per));
+    const int rem0 = (int)(e - (long long)b * 2 * per);
+    const int m = rem0 / per, rem = rem0 - m * per;
+    const int n = rem / (C::E_COLS / 2), k = (rem - n * (C::E_COLS / 2)) * 2;
+    float x[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = k + u;
+      if (n < D) {
+        if (j < N) {
+          const size_t off = ((size_t)b * N + j) * D + n;
+          x[u] = m == 0 ? -a.kp[off] : a.vp[off];
+        } else if (j == N) {
+          x[u] = m == 0 ? a.gq[(size_t)b * D + n] - a.pc[n] : a.gv[(size_t)b * D + n] - a.vc[n];
+        }
+      }
+    }
+    uint32_t hi, lo;
+    split2(x[0], x[1], hi, lo);
+    const int ks = k >> 4;
+    unsigned char *base = out + (size_t)b * table_bytes_per_shape<C>() + (size_t)(ks * 2 + m) * C::SLOT_BYTES;
+    const uint32_t in_slab = canon_off(C::DP, n, k & 15);
+    *reinterpret_cast<uint32_t *>(base + in_slab) = hi;
+    *reinterpret_cast<uint32_t *>(base + C::SLAB + in_slab) = lo;
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed,
+                    const unsigned char *__restrict__ tables, float *__restrict__ out, float *__restrict__ stats,
+                    int tpb, long long tiles, int *err) {
+  static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + C::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  unsigned char *E = smem + C::OFF_E;
+  unsigned char *stage0 = smem + C::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + C::OFF_WD0);
+  float *pcs = reinterpret_cast<float *>(smem + C::OFF_PC);
+  float *vcs = reinterpret_cast<float *>(smem + C::OFF_VC);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const int krows = a.K + 1;
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = 0.f, v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      p = a.pc[kk];
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    pcs[kk] = p;
+    vcs[kk] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < C::SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_ready, C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int W1 = 2 * C::KSTEPS;     // slots of GEMM1's weight part
+  constexpr int T1 = 2 * C::E_KSTEPS;   // slots of GEMM1's table part
+
+  if (warp == 0) {
+    // ===================== producer: weights + this shape's tables, one slot at a time =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned char *tb = tables + (size_t)(tile / tpb) * table_bytes_per_shape<C>();
+        for (int j = 0; j < W1 + T1 + C::KSTEPS; ++j, ++it) {
+          const unsigned char *src = j < W1 ? packed + (size_t)j * C::SLOT_BYTES
+                                            : (j < W1 + T1 ? tb + (size_t)(j - W1) * C::SLOT_BYTES
+                                                           : packed + (size_t)(j - T1) * C::SLOT_BYTES);
+          const int s = it % C::SLOTS;
+          const uint32_t ph = (it / C::SLOTS) & 1;
+          mbar_wait(&empty[s], ph ^ 1, err);
+          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, C::DP);
+      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo), e_addr = smem_u32(E);
+      uint32_t it = 0, ready_phase = 0;
+      auto next_slot = [&]() -> uint32_t {   // waits for the next slot of the ring, returns its shared address
+        const int s = it % C::SLOTS;
+        const uint32_t ph = (it / C::SLOTS) & 1;
+        mbar_wait(&full[s], ph, err);
+        tc_fence_after();
+        return smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
+      };
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(a_ready, ready_phase, err);
+        ready_phase ^= 1;
+        tc_fence_after();
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
+          const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
+          for (int m = 0; m < 2; ++m, ++it) {
+            const uint32_t sb = next_slot();
+            const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
+            const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+            mma_bf16(d, ah, bh, idesc, ks > 0);
+            mma_bf16(d, al, bh, idesc, true);
+            mma_bf16(d, ah, bl, idesc, true);
+            mma_commit(&empty[it % C::SLOTS]);
+          }
+        }
+        for (int ks = 0; ks < C::E_KSTEPS; ++ks) {
+          const uint64_t eh = smem_desc(e_addr + ks * 2 * lbo_a, lbo_a, 128);
+          for (int m = 0; m < 2; ++m, ++it) {
+            const uint32_t sb = next_slot();
+            const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
+            const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+            mma_bf16(d, eh, bh, idesc, true);
+            mma_bf16(d, eh, bl, idesc, true);
+            mma_commit(&empty[it % C::SLOTS]);
+          }
+        }
+        mma_commit(acc_done);
+        mbar_wait(a_ready, ready_phase, err);
+        ready_phase ^= 1;
+        tc_fence_after();
+        for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
+          const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
+          const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
+          const uint32_t sb = next_slot();
+          const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
+          mma_bf16(tmem_base, ah, bh, idesc, ks > 0);
+          mma_bf16(tmem_base, al, bh, idesc, true);
+          mma_bf16(tmem_base, ah, bl, idesc, true);
+          mma_commit(&empty[it % C::SLOTS]);
+        }
+        mma_commit(acc_done);
+      }
+    }
+  } else {
+    // ===================== workers: one TMEM lane = one pair row; NPART warps per lane quarter interleave the chunks =====
+    const int ww = warp - 2;
+    const int quarter = warp & 3;
+    const int part = ww >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t done_phase = 0;
+    constexpr int NQ = (C::CHUNKS + C::NPART - 1) / C::NPART;           // chunk rounds per thread
+    constexpr int NE = (C::E_COLS / 8 + C::NPART - 1) / C::NPART;       // one-hot chunk rounds per thread
+    const int g8 = lane & 7;
+
+    RowInfoPB ri = row_info_pb<C>(a, blockIdx.x, r, krows, tpb);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const bool row_on = ri.c >= 0;
+      // ---- operands H (bf16 hi/lo) and E (one-hot) -------------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          const int k0 = ch * 8;
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w0 = wd0s[k0 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
+          }
+          uint4 hi, lo;
+          split2(h[0], h[1], hi.x, lo.x);
+          split2(h[2], h[3], hi.y, lo.y);
+          split2(h[4], h[5], hi.z, lo.z);
+          split2(h[6], h[7], hi.w, lo.w);
+          const uint32_t off = canon_off(128, r, k0);
+          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::E_COLS / 8) {
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if ((ri.j >> 3) == ch) {   // ri.j = -1 on inactive rows: never matches
+            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+            const int w = (ri.j & 7) >> 1;
+            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(E + canon_off(128, r, ch * 8)) = e;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // ---- epilogue 1: G = relu(acc0 + pc) -> A operand ------------------------------------------------------------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          const int k0 = ch * 8;
+          float v[8], g[8];
+          tmem_ld8(trow + k0, v);
+          const float4 p0 = *reinterpret_cast<const float4 *>(pcs + k0), p1 = *reinterpret_cast<const float4 *>(pcs + k0 + 4);
+          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          // no masking needed: padded columns have zero weights and pc = 0 (G = 0), inactive rows only feed their own
+          // (ignored) rows of GEMM2
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = fmaxf(v[j] + pv[j], 0.f);
+          uint4 hi, lo;
+          split2(g[0], g[1], hi.x, lo.x);
+          split2(g[2], g[3], hi.y, lo.y);
+          split2(g[4], g[5], hi.z, lo.z);
+          split2(g[6], g[7], hi.w, lo.w);
+          const uint32_t off = canon_off(128, r, k0);
+          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // ---- while GEMM2 runs: the next tile's row description (index + coordinates: two dependent L2 reads) --------
+      const long long ci_grp = __shfl_sync(0xffffffffu, ri.c, lane & ~7);   // row 0 of the group: the centre (or -1)
+      const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
+
+      // ---- epilogue 2: softmax over the 8 rows of a centre; out = sum w * (acc1 + vc) -------------------------------------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          const int k0 = ch * 8;
+          float av[8], sv[8];
+          tmem_ld8(trow + k0, av);
+          tmem_ld8(trow + C::ACC1_COL + k0, sv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] = row_on ? av[j] : -INFINITY;
+          // transpose inside the 8-lane group: afterwards this lane holds column k0 + g8 of all 8 rows of the centre
+          group8_transpose(av, lane);
+          group8_transpose(sv, lane);
+          const int col = k0 + g8;
+          const float vcc = vcs[col];
+          float mx = av[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) mx = fmaxf(mx, av[i]);
+          float se = 0.f, ses = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = __expf(av[i] - mx);     // exp(-inf) = 0 on inactive rows (row 0 of a live centre is on)
+            se += e;
+            ses = fmaf(e, sv[i] + vcc, ses);
+          }
+          if (ci_grp >= 0 && col < D) {
+            const float inv = 1.f / se;
+            out[ci_grp * D + col] = ses * inv;
+            if (stats) {
+              stats[ci_grp * D + col] = mx;
+              stats[((long long)a.B * a.M + ci_grp) * D + col] = inv;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      ri = nxt;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <class C>
+static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *workspace, size_t ws_bytes, cudaStream_t st) {
+  const size_t tb = (size_t)a.B * table_bytes_per_shape<C>();
+  const size_t need = packed_bytes<C>() + tb + 16;
+  if (!workspace || ws_bytes < need) return NSDP_ERR_WORKSPACE;
+  unsigned char *packed = (unsigned char *)workspace;
+  unsigned char *tables = packed + packed_bytes<C>();
+  int *err = (int *)(tables + tb);
+  cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  pack_weights_kernel<C><<<64, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
+  int rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables);
+  rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  const int tpb = (a.M + C::CENTRES - 1) / C::CENTRES;
+  const long long tiles = (long long)a.B * tpb;
+  auto kern = vattn_fwd_oh_kernel<C>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, tpb, tiles, err);
+  return check_launch();
+}
+
+// the one-hot kernel serves the decoder cross-attention: global token, per-shape query (no qp), anchor tables that
+// fit the one-hot width
+static bool oh_ok(const nsdp_vattn_args &a) {
+  return a.has_global && !a.qp && a.kp && a.vp && a.gq && a.gv && a.idx && a.N + 1 <= 112 && a.K + 1 <= 8;
+}
+
 template <class C>
 static int launch(const nsdp_vattn_args &a, float *out, float *stats, void *workspace, size_t ws_bytes, cudaStream_t st) {
   const size_t need = packed_bytes<C>() + 16;
@@ -434,6 +776,20 @@ static int launch(const nsdp_vattn_args &a, float *out, float *stats, void *work
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, out, stats, tiles, err);
   return check_launch();
+}
+
+// decoder shape: worker warps per lane quarter (NSDP_FWD_NPART_DEC = 4 | 7)
+static int dec_npart_fwd() {
+  static const int v = [] {
+    const char *e = getenv("NSDP_FWD_NPART_DEC");
+    return e && atoi(e) == 4 ? 4 : 7;
+  }();
+  return v;
+}
+
+static bool no_onehot() {
+  static const bool v = [] { const char *e = getenv("NSDP_NO_ONEHOT"); return e && atoi(e) != 0; }();
+  return v;
 }
 
 // Which (DP, KR) instantiation serves these arguments; 0 = not supported by the tensor-core path.
@@ -457,7 +813,9 @@ extern "C" size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args) {
   using namespace nsdp;
   if (!args) return 0;
   switch (vtc::pick(*args)) {
-    case 1: return vtc::packed_bytes<vtc::TcCfg<208, 8>>() + 16;
+    case 1:
+      return vtc::packed_bytes<vtc::TcCfg<208, 8>>() + 16 +
+             (vtc::oh_ok(*args) ? (size_t)args->B * vtc::table_bytes_per_shape<vtc::TcCfg<208, 8, 4, true>>() : 0);
     case 2: return vtc::packed_bytes<vtc::TcCfg<128, 16>>() + 16;
     case 3: return vtc::packed_bytes<vtc::TcCfg<256, 16>>() + 16;
     case 4: return vtc::packed_bytes<vtc::TcCfg<256, 128>>() + 16;
@@ -470,7 +828,13 @@ int vattn_fwd_tc_dispatch(const nsdp_vattn_args *args, float *out, float *stats,
                           cudaStream_t st, bool *handled) {
   *handled = true;
   switch (vtc::pick(*args)) {
-    case 1: return vtc::launch<vtc::TcCfg<208, 8>>(*args, out, stats, workspace, ws_bytes, st);
+    case 1:
+      if (vtc::oh_ok(*args) && !vtc::no_onehot()) {
+        if (vtc::dec_npart_fwd() == 7)
+          return vtc::launch_oh<vtc::TcCfg<208, 8, 7, true>>(*args, out, stats, workspace, ws_bytes, st);
+        return vtc::launch_oh<vtc::TcCfg<208, 8, 4, true>>(*args, out, stats, workspace, ws_bytes, st);
+      }
+      return vtc::launch<vtc::TcCfg<208, 8>>(*args, out, stats, workspace, ws_bytes, st);
     case 2: return vtc::launch<vtc::TcCfg<128, 16>>(*args, out, stats, workspace, ws_bytes, st);
     case 3: return vtc::launch<vtc::TcCfg<256, 16>>(*args, out, stats, workspace, ws_bytes, st);
     case 4: return vtc::launch<vtc::TcCfg<256, 128>>(*args, out, stats, workspace, ws_bytes, st);

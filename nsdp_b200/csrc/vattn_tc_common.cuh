@@ -10,7 +10,7 @@ namespace vtc {
 
 using namespace umma;
 
-template <int DP_, int KR_, int NPART_ = 4>
+template <int DP_, int KR_, int NPART_ = 4, bool OH_ = false>
 struct TcCfg {
   static constexpr int DP = DP_;                 // padded channel count: K and N of every GEMM
   static constexpr int KR = KR_;                 // rows per centre inside a tile (power of two, 8..32)
@@ -18,6 +18,17 @@ struct TcCfg {
   static constexpr int SLAB = DP * 16 * 2;       // one [DP x 16] bf16 K-major weight slab
   static constexpr int STAGE_BYTES = 4 * SLAB;   // GEMM1 stage: W' hi, W' lo, Wd2 hi, Wd2 lo (GEMM2 uses half)
   static constexpr int STAGES = DP > 208 ? 2 : 4;
+  // the weight ring is addressed in SLOTS of one matrix k-step (hi slab + lo slab): GEMM1 takes two slots per k-step
+  // (W', Wd2), every other GEMM one, so the single-matrix GEMMs prefetch twice as many k-steps ahead
+  // OH ("one-hot") variant, decoder cross-attention: the per-row gathers of the K'/V anchor tables are folded into GEMM1
+  // as E * [T1 | T2], E = one-hot(neighbour index) [128 x E_COLS] bf16 (exact), T = per-shape tables streamed through the
+  // same slot ring; the epilogues then only add per-column constants. Needs N + 1 <= E_COLS (global token = row N).
+  static constexpr bool OH = OH_;
+  static constexpr int E_COLS = 112;
+  static constexpr int E_KSTEPS = E_COLS / 16;
+  static constexpr int E_BYTES = OH_ ? 128 * E_COLS * 2 : 0;
+  static constexpr int SLOTS = OH_ ? 6 : 2 * STAGES;
+  static constexpr int SLOT_BYTES = 2 * SLAB;
   static constexpr int A_HALF = 128 * DP * 2;    // bytes of the hi (or lo) A operand
   static constexpr int NPART = NPART_;           // worker warps per TMEM lane quarter (they split the columns)
   static constexpr int WORKER_WARPS = 4 * NPART;
@@ -29,8 +40,9 @@ struct TcCfg {
   static constexpr int CENTRES = 128 / KR;
   // dynamic shared memory carve-up (bytes)
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_STAGE = OFF_A + 2 * A_HALF;
-  static constexpr int OFF_WD0 = OFF_STAGE + STAGES * STAGE_BYTES;   // float4[DP]
+  static constexpr int OFF_E = OFF_A + 2 * A_HALF;
+  static constexpr int OFF_STAGE = OFF_E + E_BYTES;
+  static constexpr int OFF_WD0 = OFF_STAGE + SLOTS * SLOT_BYTES;     // float4[DP]
   static constexpr int OFF_PC = OFF_WD0 + DP * 16;                   // float[DP]
   static constexpr int OFF_VC = OFF_PC + DP * 4;                     // float[DP]
   static constexpr int OFF_RED = OFF_VC + DP * 4;                    // float[3][4][DP] cross-warp softmax (KR == 128)
@@ -45,6 +57,57 @@ struct RowInfo {
   int n;       // flattened source row, or -(b+1) for the global row
   float rx, ry, rz, flag;
 };
+
+// Row description under PER-SHAPE tiling (OH kernels): tile t covers centres [(t % tpb) * CENTRES, +CENTRES) of shape
+// b = t / tpb, so a tile never straddles two shapes and the producer can stream that shape's tables.
+struct RowInfoPB {
+  int c;       // flattened centre b*M + m, -1 = inactive
+  int j;       // source index inside the shape (0..N-1), N for the global-token row, -1 = inactive
+  float rx, ry, rz, flag;
+};
+
+template <class C>
+__device__ __forceinline__ RowInfoPB row_info_pb(const nsdp_vattn_args &a, long long tile, int r, int krows, int tpb) {
+  RowInfoPB ri;
+  ri.c = -1; ri.j = -1; ri.rx = ri.ry = ri.rz = 0.f; ri.flag = 0.f;
+  const int b = (int)(tile / tpb);
+  const int m = (int)(tile - (long long)b * tpb) * C::CENTRES + r / C::KR;
+  const int t = r % C::KR;
+  if (b < a.B && m < a.M && t < krows) {
+    const long long ci = (long long)b * a.M + m;
+    ri.c = (int)ci;
+    if (t < a.K) {
+      const int j = a.idx ? a.idx[ci * a.K + t] : t;
+      ri.j = j;
+      const float *xc = a.xyz_c + ci * 3;
+      const float *xn = a.xyz_n + ((size_t)b * a.N + j) * 3;
+      ri.rx = a.sign * (xc[0] - xn[0]);
+      ri.ry = a.sign * (xc[1] - xn[1]);
+      ri.rz = a.sign * (xc[2] - xn[2]);
+      ri.flag = 1.f;
+    } else {
+      ri.j = a.N;
+    }
+  }
+  return ri;
+}
+
+// In-place 8 x 8 transpose inside every group of 8 consecutive lanes: before, lane l holds row l (v[i] = column i);
+// after, lane l holds column l (v[i] = row i). 12 shuffles.
+__device__ __forceinline__ void group8_transpose(float (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i & s) continue;
+      const float send = up ? v[i] : v[i | s];
+      const float recv = __shfl_xor_sync(full, send, s);
+      if (up) v[i] = recv; else v[i | s] = recv;
+    }
+  }
+}
 
 template <class C>
 __device__ __forceinline__ RowInfo row_info(const nsdp_vattn_args &a, long long tile, int r, int krows) {
