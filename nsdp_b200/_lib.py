@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libnsdp_b200.so")
+LIB_PATH = os.environ.get("NSDP_B200_LIB") or os.path.join(_PKG, "lib", "libnsdp_b200.so")  # override: A/B builds
 
 c_float_p = C.c_void_p
 c_int_p = C.c_void_p

@@ -16,14 +16,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "lib", "obj")
-LIB = os.path.join(PKG, "lib", "libnsdp_b200.so")
+# NSDP_BUILD_VARIANT=<name> + NSDP_BUILD_DEFS="-DX -DY" builds an A/B copy (lib/libnsdp_b200_<name>.so) next to the product
+VARIANT = os.environ.get("NSDP_BUILD_VARIANT", "")
+OBJ = os.path.join(PKG, "lib", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(PKG, "lib", "libnsdp_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v", "-I", INCLUDE]
+         "-Xptxas", "-v", "-I", INCLUDE] + (os.environ.get("NSDP_BUILD_DEFS", "").split() if VARIANT else [])
 
 
 def _deps_mtime() -> float:

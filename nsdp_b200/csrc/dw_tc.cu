@@ -28,8 +28,7 @@ constexpr int MAX_JOBS = 24;
 struct Params {
   Job jobs[MAX_JOBS];
   int njobs;
-  int splits;              // CTAs per job
-  long long tiles;         // row tiles per job (same for all jobs of a launch)
+  int cta_begin[MAX_JOBS + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split the tile range of job j
   int stages;              // ring depth (<= MAX_STAGES)
   int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
   int *err;
@@ -41,11 +40,15 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   const int STAGES = p.stages;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int jid = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  int jid = 0;
+  while (jid + 1 < p.njobs && (int)blockIdx.x >= p.cta_begin[jid + 1]) ++jid;
+  const int splits = p.cta_begin[jid + 1] - p.cta_begin[jid], split = (int)blockIdx.x - p.cta_begin[jid];
   const Job job = p.jobs[jid];
-  const long long t0 = p.tiles * split / p.splits, t1 = p.tiles * (split + 1) / p.splits;
+  const long long jt = job.t1 - job.t0;
+  const long long t0 = job.t0 + jt * split / splits, t1 = job.t0 + jt * (split + 1) / splits;
   const uint32_t xs = (uint32_t)job.wx * 32, ys = (uint32_t)job.wy * 32;  // slab bytes
-  const bool x_lo = p.terms >= 2, y_lo = p.terms >= 3;   // which lo slabs are streamed at all
+  const uint32_t xk = job.x_lo ? 2 * xs : xs, yk = job.y_lo ? 2 * ys : ys;   // k-step pitch inside a staged tile
+  const bool x_lo = job.x_lo && p.terms >= 2, y_lo = job.y_lo && p.terms >= 3;   // which lo slabs are streamed at all
   const uint32_t xb = x_lo ? 2 * xs : xs, yb = y_lo ? 2 * ys : ys;
   const uint32_t stage_bytes = xb + yb;
   const int mtiles = job.wx > 128 ? 2 : 1;
@@ -66,48 +69,53 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   const bool has_work = t1 > t0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long t = t0; t < t1; ++t) {
-        const unsigned char *xt = job.x + (size_t)t * 512 * job.wx;
-        const unsigned char *yt = job.y + (size_t)t * 512 * job.wy;
-        for (int ks = 0; ks < 8; ++ks, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1, p.err);
-          mbar_arrive_expect_tx(&full[s], stage_bytes);
-          unsigned char *dst = smem + (size_t)s * stage_bytes;
-          bulk_g2s(dst, xt + (size_t)ks * 2 * xs, xb, &full[s]);
-          bulk_g2s(dst + xb, yt + (size_t)ks * 2 * ys, yb, &full[s]);
-        }
+    // Producer: PL lanes issue the bulk copies, lane l serving k-steps l, l + PL, ... (one thread sustains only about
+    // one copy per ~500 cycles: the wait / expect_tx / issue chain is serial; measured with tools/micro/stream_bw.cu)
+    const int PL = STAGES >= 4 ? STAGES / 2 : 1;
+    if (lane < PL) {
+      const long long total = (t1 - t0) * 8;
+      for (long long it = lane; it < total; it += PL) {
+        const long long t = t0 + (it >> 3);
+        const int ks = (int)(it & 7);
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err);
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        unsigned char *dst = smem + (size_t)s * stage_bytes;
+        bulk_g2s(dst, job.x + (size_t)t * 8 * xk + (size_t)ks * xk, xb, &full[s]);
+        bulk_g2s(dst + xb, job.y + (size_t)t * 8 * yk + (size_t)ks * yk, yb, &full[s]);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    // MMA issuer: whole warp runs the loop and the waits, one elected lane issues (elect_one: straight UTCHMMA issue);
+    // descriptors advance by adds, the ring position is a running counter
+    if (has_work) {
       const uint32_t idesc = idesc_bf16_mn(128, job.wy);
-      uint32_t it = 0;
+      const uint64_t x0 = smem_desc(smem_u32(smem), 128, 256);
+      const uint32_t stage16 = stage_bytes >> 4;
+      uint32_t slot = 0, slot_phase = 0;
       bool first = true;
-      for (long long t = t0; t < t1; ++t) {
-        for (int ks = 0; ks < 8; ++ks, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph, p.err);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t yh = smem_desc(sb + xb, 128, 256), yl = smem_desc(sb + xb + ys, 128, 256);
+      const long long total = (t1 - t0) * 8;
+      for (long long it = 0; it < total; ++it) {
+        mbar_wait(&full[slot], slot_phase, p.err);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t xh0 = x0 + (uint64_t)slot * stage16;
+          const uint64_t yh = xh0 + (xb >> 4), yl = yh + (ys >> 4);
           for (int j = 0; j < mtiles; ++j) {
             // M-tile j = output rows [128j, 128j+128) = column groups 16j.. of the X slab (4096 bytes further)
-            const uint64_t xh = smem_desc(sb + j * 4096, 128, 256), xl = smem_desc(sb + xs + j * 4096, 128, 256);
+            const uint64_t xh = xh0 + (uint64_t)j * (4096 >> 4), xl = xh + (xs >> 4);
             const uint32_t d = tmem_base + j * 256;
             mma_bf16(d, xh, yh, idesc, !first);
             if (x_lo) mma_bf16(d, xl, yh, idesc, true);
             if (y_lo) mma_bf16(d, xh, yl, idesc, true);
           }
-          first = false;
-          mma_commit(&empty[s]);
+          mma_commit(&empty[slot]);
         }
+        first = false;
+        if (++slot == (uint32_t)STAGES) { slot = 0; slot_phase ^= 1; }
       }
-      mma_commit(&acc_done);
+      if (elect_one()) mma_commit(&acc_done);
     }
   } else if (has_work) {
     {
@@ -223,32 +231,47 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   using namespace dwtc;
   if (njobs <= 0 || njobs > MAX_JOBS || tiles <= 0) return NSDP_ERR_INVALID_ARGUMENT;
   Params p;
-  int maxw = 0;
+  p.terms = dw_terms();
+  size_t max_stage = 0;
+  double cost[MAX_JOBS], total = 0.0;
   for (int i = 0; i < njobs; ++i) {
-    p.jobs[i] = jobs[i];
-    if (jobs[i].wx % 16 || jobs[i].wy % 16 || jobs[i].wx > 256 || jobs[i].wy > 256) return NSDP_ERR_UNSUPPORTED;
-    maxw = jobs[i].wx + jobs[i].wy > maxw ? jobs[i].wx + jobs[i].wy : maxw;
+    Job j = jobs[i];
+    if (j.wx % 16 || j.wy % 16 || j.wx > 256 || j.wy > 256) return NSDP_ERR_UNSUPPORTED;
+    if (j.t1 < 0) { j.t0 = 0; j.t1 = tiles; }
+    if (j.t1 <= j.t0) return NSDP_ERR_INVALID_ARGUMENT;
+    p.jobs[i] = j;
+    // bytes one k-step brings into shared memory (the reduction is bandwidth-bound: CTAs are dealt out by bytes)
+    const size_t stage = (size_t)32 * (j.wx * ((j.x_lo && p.terms >= 2) ? 2 : 1) + j.wy * ((j.y_lo && p.terms >= 3) ? 2 : 1));
+    max_stage = stage > max_stage ? stage : max_stage;
+    cost[i] = (double)stage * (double)(j.t1 - j.t0);
+    total += cost[i];
   }
   p.njobs = njobs;
-  int splits = num_sms() / njobs;
-  if (splits < 1) splits = 1;
-  if (splits > tiles) splits = (int)tiles;
-  p.splits = splits;
-  p.tiles = tiles;
-  p.terms = dw_terms();
+  // CTAs per job: proportional to bytes, at least 1, at most the job's tile count; about one CTA per SM in total
+  const int budget = num_sms() > njobs ? num_sms() : njobs;
+  int ctas = 0;
+  p.cta_begin[0] = 0;
+  for (int i = 0; i < njobs; ++i) {
+    long long n = (long long)(cost[i] / total * budget);
+    const long long jt = p.jobs[i].t1 - p.jobs[i].t0;
+    if (n < 1) n = 1;
+    if (n > jt) n = jt;
+    ctas += (int)n;
+    p.cta_begin[i + 1] = ctas;
+  }
   p.err = err;
-  // stage = 2*32*(wx+wy) bytes; + slack for the M-tile-1 overrun. The ring is as deep as shared memory allows: the
-  // operand tiles stream from HBM (several microseconds of latency under load), 4 stages left the SMs waiting
-  int stages = (int)((227 * 1024 - 4096 - 1024) / ((size_t)64 * maxw));
+  // The ring is as deep as shared memory allows (+ slack for the M-tile-1 overrun): the operand tiles stream from HBM
+  // (several microseconds of latency under load), 4 stages left the SMs waiting
+  int stages = (int)((227 * 1024 - 4096 - 1024) / max_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return NSDP_ERR_UNSUPPORTED;
   static const int forced = [] { const char *e = getenv("NSDP_DW_STAGES"); return e ? atoi(e) : 0; }();
   if (forced >= 2 && forced < stages) stages = forced;
   p.stages = stages;
-  const size_t smem = (size_t)stages * 64 * maxw + 4096;
+  const size_t smem = (size_t)stages * max_stage + 4096;
   cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
-  dw_tc_kernel<<<njobs * splits, THREADS, smem, st>>>(p);
+  dw_tc_kernel<<<ctas, THREADS, smem, st>>>(p);
   return check_launch();
 }
 

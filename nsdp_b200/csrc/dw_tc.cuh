@@ -18,6 +18,11 @@ struct Job {
   float *gsum;
   int g_kr, g_M;
   long long g_centre0;
+  // staged precision per operand: 1 = [hi slab][lo slab] per k-step (bf16x2, fp32-grade), 0 = hi slab only (plain bf16;
+  // used for exact operands such as one-hot tiles and for reductions over millions of rows)
+  int x_lo = 1, y_lo = 1;
+  // tile range of this job inside the staging buffers (tile index relative to x / y); t1 < 0 = all tiles of the launch
+  long long t0 = 0, t1 = -1;
 };
 
 }  // namespace dwtc

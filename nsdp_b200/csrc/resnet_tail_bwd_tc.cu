@@ -206,52 +206,72 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
 
   if (warp == 0) {
     // ===================== weight producer: streams the packed image once per tile, in order =====================
-    if (lane == 0) {
-      uint32_t it = 0;
+    // PL lanes share the bulk copies (lane l serves stages l, l + PL, ...): one thread sustains only about one copy per
+    // ~500 cycles, less than the tensor pipe drains
+    constexpr int PL = 2;
+    if (lane < PL) {
       const size_t fwd_bytes = fwd_region_bytes<C>(nb);
-      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        auto push = [&](const unsigned char *src, uint32_t bytes) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1, err);
-          mbar_arrive_expect_tx(&full[s], bytes);
-          bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, src, bytes, &full[s]);
-          ++it;
-        };
-        const int nfwd = (1 + nb) * C::KS_C + 2 * nb * KS_H;
-        for (int st = 0; st < nfwd; ++st) push(packed + (size_t)st * ST_H, ST_H);
-        const unsigned char *p = packed + fwd_bytes;
-        for (int i = nb - 1; i >= 0; --i) {
-          for (int ks = 0; ks < 2 * KS_H; ++ks, p += ST_H) push(p, ST_H);      // w1b_i, w0b_i
-          for (int ks = 0; ks < KS_H; ++ks, p += ST_C) push(p, ST_C);          // wcb_{i+1}
+      const int nfwd = (1 + nb) * C::KS_C + 2 * nb * KS_H;
+      constexpr int PER_BLK = 3 * KS_H;                                   // w1b_i, w0b_i (2 KS_H x ST_H), wcb_{i+1} (KS_H x ST_C)
+      constexpr size_t BLK_BYTES = (size_t)2 * KS_H * ST_H + (size_t)KS_H * ST_C;
+      const int per_tile = nfwd + nb * PER_BLK + KS_H;                    // ... + wcb_0
+      const long long first = tile_begin + blockIdx.x;
+      const long long my_tiles = first < tile_end ? (tile_end - first + gridDim.x - 1) / gridDim.x : 0;
+      const long long total = my_tiles * per_tile;
+      for (long long it = lane; it < total; it += PL) {
+        const int st = (int)(it % per_tile);
+        const unsigned char *src;
+        uint32_t bytes;
+        if (st < nfwd) {
+          src = packed + (size_t)st * ST_H; bytes = ST_H;
+        } else {
+          const int u = st - nfwd, blk = u / PER_BLK, w = u - blk * PER_BLK;
+          if (blk < nb) {
+            src = packed + fwd_bytes + (size_t)blk * BLK_BYTES + (w < 2 * KS_H ? (size_t)w * ST_H : (size_t)2 * KS_H * ST_H + (size_t)(w - 2 * KS_H) * ST_C);
+            bytes = w < 2 * KS_H ? ST_H : ST_C;
+          } else {
+            src = packed + fwd_bytes + (size_t)nb * BLK_BYTES + (size_t)(u - nb * PER_BLK) * ST_C; bytes = ST_C;
+          }
         }
-        for (int ks = 0; ks < KS_H; ++ks, p += ST_C) push(p, ST_C);            // wcb_0
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(stage0 + (size_t)s * C::STAGE_BYTES, src, bytes, &full[s]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp runs loops and waits, one elected lane issues (elect_one: straight UTCHMMA issue); descriptors advance
+    // by adds, the ring position is a running counter (the issuing thread must keep ahead of the tensor pipe)
+    {
       const uint32_t idesc_h = idesc_bf16(128, H), idesc_c = idesc_bf16(128, C::CP);
-      const uint32_t lbo_a = 128 * 16;
-      const uint32_t lhi = smem_u32(L_hi), llo = smem_u32(L_lo), xhi = smem_u32(X_hi), xlo = smem_u32(X_lo);
-      uint32_t it = 0, ready_phase = 0;
-      // A (hi/lo, `ksteps` k-steps) x the next `ksteps` weight stages of N = nrows -> TMEM column `col`
-      auto gemm = [&](uint32_t a_hi, uint32_t a_lo, int ksteps, int nrows, uint32_t idesc, uint32_t col, bool fresh) {
+      constexpr uint32_t lbo_a = 128 * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t lhi = smem_desc(smem_u32(L_hi), lbo_a, 128), llo = smem_desc(smem_u32(L_lo), lbo_a, 128);
+      const uint64_t xhi = smem_desc(smem_u32(X_hi), lbo_a, 128), xlo = smem_desc(smem_u32(X_lo), lbo_a, 128);
+      const uint32_t stage_addr = smem_u32(stage0);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+      // A (hi/lo descriptors, `ksteps` k-steps) x the next `ksteps` weight stages of N = nrows -> TMEM column `col`
+      auto gemm = [&](uint64_t a_hi, uint64_t a_lo, int ksteps, int nrows, uint32_t idesc, uint32_t col, bool fresh) {
         const uint32_t lbo_b = nrows * 16, slab = nrows * 32;
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph, err);
+        const uint64_t bh0 = smem_desc(stage_addr, lbo_b, 128);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[slot], slot_phase, err);
           tc_fence_after();
-          const uint32_t sb = smem_u32(stage0 + (size_t)s * C::STAGE_BYTES);
-          const uint64_t ah = smem_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t al = smem_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + slab, lbo_b, 128);
-          mma_bf16(tmem_base + col, ah, bh, idesc, !(fresh && ks == 0));
-          mma_bf16(tmem_base + col, al, bh, idesc, true);
-          mma_bf16(tmem_base + col, ah, bl, idesc, true);
-          mma_commit(&empty[s]);
+          if (elect_one()) {
+            const uint64_t ah = a_hi + ks * A_STEP, al = a_lo + ks * A_STEP;
+            const uint64_t bh = bh0 + (uint64_t)slot * (C::STAGE_BYTES >> 4);
+            mma_bf16(tmem_base + col, ah, bh, idesc, !(fresh && ks == 0));
+            mma_bf16(tmem_base + col, al, bh, idesc, true);
+            mma_bf16(tmem_base + col, ah, bh + (slab >> 4), idesc, true);
+            mma_commit(&empty[slot]);
+          }
+          if (++slot == STAGES) { slot = 0; slot_phase ^= 1; }
         }
+      };
+      auto commit_acc = [&]() {
+        if (elect_one()) mma_commit(acc_done);
       };
       auto wait_ready = [&]() {
         mbar_wait(a_ready, ready_phase, err);
@@ -263,30 +283,30 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
         wait_ready();
         gemm(lhi, llo, C::KS_C, H, idesc_h, 0, true);
         if (nb > 0) gemm(lhi, llo, C::KS_C, H, idesc_h, 0, false);
-        mma_commit(acc_done);
+        commit_acc();
         for (int i = 0; i < nb; ++i) {
           wait_ready();
           gemm(xhi, xlo, KS_H, H, idesc_h, ACC_H, true);
-          mma_commit(acc_done);
+          commit_acc();
           if (i + 1 < nb) gemm(lhi, llo, C::KS_C, H, idesc_h, 0, false);
           wait_ready();
           gemm(xhi, xlo, KS_H, H, idesc_h, 0, false);
-          mma_commit(acc_done);
+          commit_acc();
         }
         // ---- backward ----
         for (int i = nb - 1; i >= 0; --i) {
           wait_ready();                                            // dnet (= d net_{i+1}) operand in X
           if (i < nb - 1) gemm(xhi, xlo, KS_H, C::CP, idesc_c, ACC_DLAT, i == nb - 2);   // dlat += dn_{i+1} * Wc_{i+2}
           gemm(xhi, xlo, KS_H, H, idesc_h, ACC_H, true);           // dy = dnet * W1_i
-          mma_commit(acc_done);
+          commit_acc();
           wait_ready();                                            // dhh operand
           gemm(xhi, xlo, KS_H, H, idesc_h, ACC_H, true);           // dx = dhh * W0_i
-          mma_commit(acc_done);
+          commit_acc();
         }
         wait_ready();                                              // dn_0 operand
         if (nb > 0) gemm(xhi, xlo, KS_H, C::CP, idesc_c, ACC_DLAT, nb == 1);             // dlat += dn_0 * Wc_1
         gemm(xhi, xlo, KS_H, C::CP, idesc_c, ACC_DLAT, nb == 0);                          // dlat += dn_0 * Wc_0
-        mma_commit(acc_done);
+        commit_acc();
       }
     }
   } else {
@@ -463,7 +483,7 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-constexpr long long kSegmentTiles = 512;   // staging: (CP + 22*128 + 16) * 512 B per tile ~ 1.5 MB -> 0.8 GB per segment
+constexpr long long kSegmentTiles = 592;   // 4 x 148 SMs: whole waves. staging: (CP + 22*128 + 16) * 512 B per tile ~ 1.5 MB -> 0.8 GB per segment
 
 template <class C>
 static size_t staged_bytes_per_tile(int nb) {

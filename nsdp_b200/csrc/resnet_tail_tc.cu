@@ -155,40 +155,50 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
   const int per_tile = stages_per_tile<C>(nb);
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int st = 0; st < per_tile; ++st, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1, err);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          bulk_g2s(stage0 + (size_t)s * STAGE_BYTES, packed + (size_t)st * STAGE_BYTES, STAGE_BYTES, &full[s]);
-        }
+    // weight producer: PL lanes share the bulk copies (lane l serves stages l, l + PL, ...): one thread sustains only
+    // about one copy per ~500 cycles, the tensor pipe drains an 8 KB stage in ~200
+    constexpr int PL = 2;
+    if (lane < PL) {
+      const long long my_tiles = (long long)blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const long long total = my_tiles * per_tile;
+      for (long long it = lane; it < total; it += PL) {
+        const int st = (int)(it % per_tile);
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        bulk_g2s(stage0 + (size_t)s * STAGE_BYTES, packed + (size_t)st * STAGE_BYTES, STAGE_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: whole warp runs loops and waits, one elected lane issues (elect_one: straight UTCHMMA issue);
+    // descriptors advance by adds, the ring position is a running counter
+    {
       const uint32_t idesc = idesc_bf16(128, H);
-      const uint32_t lbo_a = 128 * 16, lbo_b = H * 16;
-      const uint32_t lhi = smem_u32(L_hi), llo = smem_u32(L_lo), xhi = smem_u32(X_hi), xlo = smem_u32(X_lo);
-      uint32_t it = 0, ready_phase = 0;
-      // one GEMM: A (hi/lo at a_hi/a_lo, ksteps) x next `ksteps` weight stages -> tmem column `col`
-      auto gemm = [&](uint32_t a_hi, uint32_t a_lo, int ksteps, uint32_t col, bool fresh) {
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph, err);
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = H * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t lhi = smem_desc(smem_u32(L_hi), lbo_a, 128), llo = smem_desc(smem_u32(L_lo), lbo_a, 128);
+      const uint64_t xhi = smem_desc(smem_u32(X_hi), lbo_a, 128), xlo = smem_desc(smem_u32(X_lo), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+      // one GEMM: A (hi/lo descriptors, ksteps) x next `ksteps` weight stages -> tmem column `col`
+      auto gemm = [&](uint64_t a_hi, uint64_t a_lo, int ksteps, uint32_t col, bool fresh) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[slot], slot_phase, err);
           tc_fence_after();
-          const uint32_t sb = smem_u32(stage0 + (size_t)s * STAGE_BYTES);
-          const uint64_t ah = smem_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t al = smem_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + SLAB, lbo_b, 128);
-          mma_bf16(tmem_base + col, ah, bh, idesc, !(fresh && ks == 0));
-          mma_bf16(tmem_base + col, al, bh, idesc, true);
-          mma_bf16(tmem_base + col, ah, bl, idesc, true);
-          mma_commit(&empty[s]);
+          if (elect_one()) {
+            const uint64_t ah = a_hi + ks * A_STEP, al = a_lo + ks * A_STEP;
+            const uint64_t bh = bh0 + (uint64_t)slot * (STAGE_BYTES >> 4);
+            mma_bf16(tmem_base + col, ah, bh, idesc, !(fresh && ks == 0));
+            mma_bf16(tmem_base + col, al, bh, idesc, true);
+            mma_bf16(tmem_base + col, ah, bh + (SLAB >> 4), idesc, true);
+            mma_commit(&empty[slot]);
+          }
+          if (++slot == STAGES) { slot = 0; slot_phase ^= 1; }
         }
+      };
+      auto commit_acc = [&]() {
+        if (elect_one()) mma_commit(acc_done);
       };
       auto wait_ready = [&]() {
         mbar_wait(a_ready, ready_phase, err);
@@ -199,15 +209,15 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
         wait_ready();                                   // lat operand written
         gemm(lhi, llo, C::KS_C, 0, true);               // init_enc
         if (nb > 0) gemm(lhi, llo, C::KS_C, 0, false);  // fc_c[0]
-        mma_commit(acc_done);
+        commit_acc();
         for (int i = 0; i < nb; ++i) {
           wait_ready();                                 // x = relu(net + bsum_i)
           gemm(xhi, xlo, KS_H, ACC1_COL, true);         // fc_0[i] -> acc1
-          mma_commit(acc_done);
+          commit_acc();
           if (i + 1 < nb) gemm(lhi, llo, C::KS_C, 0, false);  // fc_c[i+1] -> acc0 while the workers build y
           wait_ready();                                 // y = relu(h + b0_i)
           gemm(xhi, xlo, KS_H, 0, false);               // fc_1[i] -> acc0
-          mma_commit(acc_done);
+          commit_acc();
         }
       }
     }

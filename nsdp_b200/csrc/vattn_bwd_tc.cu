@@ -85,6 +85,8 @@ __global__ void pack_bwd_weights_kernel(const float *__restrict__ wpt, const flo
   }
 }
 
+constexpr int dwtc_max_jobs = 24;   // = dwtc::MAX_JOBS (dw_tc.cu)
+
 struct Staging {
   unsigned char *h, *g, *da, *dgp, *ds;  // each: tiles_in_segment * staged_tile_bytes
 };
@@ -186,27 +188,33 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {
     // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;   // slot counter (one slot = one matrix k-step: hi slab + lo slab)
-      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        // the packed image is consumed front to back: GEMM1 takes 2 slots per k-step, GEMM2..4b one
-        const unsigned char *src = packed;
-        for (int j = 0; j < 6 * C::KSTEPS; ++j, ++it, src += C::SLOT_BYTES) {
-          const int s = it % C::SLOTS;
-          const uint32_t ph = (it / C::SLOTS) & 1;
-          mbar_wait(&empty[s], ph ^ 1, err);
-          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
-          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
-        }
+    // the packed image is consumed front to back once per tile (GEMM1 takes 2 slots per k-step, GEMM2..4b one); PL lanes
+    // share the copies (lane l serves slots l, l + PL, ...), see vattn_fwd_oh_kernel
+    constexpr int PL = C::SLOTS / 2;
+    constexpr int PER_TILE = 6 * C::KSTEPS;
+    if (lane < PL) {
+      const long long first = tile_begin + blockIdx.x;
+      const long long my_tiles = first < tile_end ? (tile_end - first + gridDim.x - 1) / gridDim.x : 0;
+      const long long total = my_tiles * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const int j = (int)(it % PER_TILE);
+        const int s = (int)(it % C::SLOTS);
+        const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+        bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, packed + (size_t)j * C::SLOT_BYTES, C::SLOT_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp runs loops and waits, one elected lane issues (see vattn_bwd_oh_kernel)
+    {
       const uint32_t idesc = idesc_bf16(128, C::DP);
-      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
-      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo);
-      uint32_t it = 0, ready_phase = 0;
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
       for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int gi = 0; gi < 5; ++gi) {
           mbar_wait(a_ready, ready_phase, err);
@@ -216,24 +224,23 @@ vattn_bwd_tc_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           const uint32_t dcol = (gi == 3 || gi == 4) ? C::ACC1_COL : 0;
           const bool keep = gi == 4;  // GEMM4b adds to GEMM4a's result
           for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
-            for (int m = 0; m < (gi == 0 ? 2 : 1); ++m, ++it) {   // GEMM1: W' -> acc0, then Wd2 -> acc1
-              const int s = it % C::SLOTS;
-              const uint32_t ph = (it / C::SLOTS) & 1;
-              mbar_wait(&full[s], ph, err);
+            for (int m = 0; m < (gi == 0 ? 2 : 1); ++m) {   // GEMM1: W' -> acc0, then Wd2 -> acc1
+              mbar_wait(&full[slot], slot_phase, err);
               tc_fence_after();
-              const uint32_t sb = smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
-              const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
-              const uint32_t d = tmem_base + (m ? C::ACC1_COL : dcol);
-              const bool acc = keep || ks > 0;
-              mma_bf16(d, ah, bh, idesc, acc);
-              mma_bf16(d, al, bh, idesc, true);
-              mma_bf16(d, ah, bl, idesc, true);
-              mma_commit(&empty[s]);
+              if (elect_one()) {
+                const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+                const uint64_t bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
+                const uint32_t d = tmem_base + (m ? C::ACC1_COL : dcol);
+                const bool acc = keep || ks > 0;
+                mma_bf16(d, ah, bh, idesc, acc);
+                mma_bf16(d, al, bh, idesc, true);
+                mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+                mma_commit(&empty[slot]);
+              }
+              if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
             }
           }
-          mma_commit(acc_done);
+          if (elect_one()) mma_commit(acc_done);
         }
       }
     }
@@ -579,6 +586,616 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
   return check_launch();
 }
 
+
+// =====================================================================================================================
+// OH variant of the chain kernel (decoder cross-attention; forward counterpart: vattn_fwd_oh_kernel in vattn_tc.cu).
+//   * GEMM1 = [H | E] * [W' ; T1_b] -> acc0 and [H | E] * [Wd2 ; T2_b] -> acc1: no per-row gathers of the anchor tables,
+//     the epilogues add per-column constants only (G = relu(acc0 + pc), s = acc1 + vc).
+//   * the scatters d_kp / d_vp / d_gq / d_gv become products with the same one-hot operand, dT1_b = E^T dGP and
+//     dT2_b = E^T dS, reduced by dw_tc_kernel from the staged tiles like the weight gradients (no atomics).
+//   * dS and dGP are needed a second time as A operands one GEMM later: they are PARKED in TMEM (already split into bf16
+//     hi/lo words, in the columns of the accumulator they were derived from) instead of being re-read from global memory.
+//   * the per-centre inputs of the softmax backward (max, 1/sum, d_out, out) are loaded one half-chunk ahead.
+//   * staging precision: `lo` = 0 stages only the bf16 hi half of every operand tile (reductions over millions of rows).
+// =====================================================================================================================
+#ifdef NSDP_TRACE
+// timeline of CTA 0 (debug builds only): (event id, clock64) pairs appended to a buffer whose address comes from the
+// environment (NSDP_TRACE_PTR, a device pointer to >= 64 KB of zeroed memory; word 0 = number of events)
+#define TR(id)                                                                              \
+  do {                                                                                      \
+    if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                              \
+      const unsigned long long n_ = atomicAdd(trace, 1ull);                                 \
+      if (n_ < 4000) { trace[1 + 2 * n_] = (unsigned long long)(id); trace[2 + 2 * n_] = (unsigned long long)clock64(); } \
+    }                                                                                       \
+  } while (0)
+#else
+#define TR(id) do { } while (0)
+#endif
+
+struct OhStaging {
+  unsigned char *h, *g, *da, *dgp, *ds, *e;
+  int lo;   // 1: [hi slab][lo slab] per k-step, 0: hi slab only
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, const float *__restrict__ stats,
+                    const float *__restrict__ dout, const nsdp_vattn_grads g, const unsigned char *__restrict__ packed,
+                    const unsigned char *__restrict__ tables, const OhStaging stg, int tpb, long long tile_begin,
+                    long long tile_end, int *err, unsigned long long *trace) {
+  static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
+  using L = BwdLayout<C>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + L::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  unsigned char *E = smem + L::OFF_E;
+  float *scratch = reinterpret_cast<float *>(smem + L::OFF_A);  // aliases A once GEMM4b has consumed it
+  unsigned char *stage0 = smem + L::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + L::OFF_WD0);
+  float *pcs = reinterpret_cast<float *>(smem + L::OFF_PC);
+  float *vcs = reinterpret_cast<float *>(smem + L::OFF_VC);
+  float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
+  float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const int krows = a.K + 1;
+  const long long BM = (long long)a.B * a.M;
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = 0.f, v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      p = a.pc[kk];
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    pcs[kk] = p;
+    vcs[kk] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < C::SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_ready, C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int W1 = 2 * C::KSTEPS;     // slots of GEMM1's weight part (W', Wd2 per k-step)
+  constexpr int T1 = 2 * C::E_KSTEPS;   // slots of GEMM1's table part (T1_b, T2_b per k-step)
+
+  if (warp == 0) {
+    // ===================== producer: weights + this shape's tables, one slot at a time =====================
+    // PL lanes share the work (lane l serves slots l, l + PL, ...), see vattn_fwd_oh_kernel
+    constexpr int PL = C::SLOTS / 2;
+    constexpr int PER_TILE = T1 + 6 * C::KSTEPS;
+    if (lane < PL) {
+      const long long first = tile_begin + blockIdx.x;
+      const long long my_tiles = first < tile_end ? (tile_end - first + gridDim.x - 1) / gridDim.x : 0;
+      const long long total = my_tiles * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const long long tile = first + (it / PER_TILE) * gridDim.x;
+        const int j = (int)(it % PER_TILE);
+        const unsigned char *tb = tables + (size_t)(tile / tpb) * table_bytes_per_shape<C>();
+        const unsigned char *src = j < W1 ? packed + (size_t)j * C::SLOT_BYTES
+                                          : (j < W1 + T1 ? tb + (size_t)(j - W1) * C::SLOT_BYTES
+                                                         : packed + (size_t)(j - T1) * C::SLOT_BYTES);
+        const int s = (int)(it % C::SLOTS);
+        const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+        bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the loops and the waits; one elected lane issues. Per slot the issuing thread must stay under
+    // the ~310 cycles the tensor pipe needs for three MMAs, so the descriptors are advanced by adds (the start-address
+    // field counts 16-byte units) and the ring position is a running counter.
+    {
+      const uint32_t idesc = idesc_bf16(128, C::DP);
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;            // one k-step further inside an A operand
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+      auto wait_operand = [&]() {
+        mbar_wait(a_ready, ready_phase, err);
+        ready_phase ^= 1;
+        tc_fence_after();
+      };
+      // waits for the next slot of the ring; returns the B descriptor of its hi slab (lo slab = + SLAB / 16)
+      auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
+        mbar_wait(&full[slot], slot_phase, err);
+        tc_fence_after();
+        bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
+        release = &empty[slot];
+        if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
+      };
+      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        // ---- GEMM1: [H | E] -> acc0 (W', T1), acc1 (Wd2, T2) ----
+        TR(100);
+        wait_operand();
+        TR(101);
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint64_t bh, *rel;
+            take_slot(bh, rel);
+            if (elect_one()) {
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+              mma_bf16(d, ah, bh, idesc, ks > 0);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(rel);
+            }
+          }
+        }
+        for (int ks = 0; ks < C::E_KSTEPS; ++ks) {
+          const uint64_t eh = eh0 + ks * A_STEP;
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint64_t bh, *rel;
+            take_slot(bh, rel);
+            if (elect_one()) {
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+              mma_bf16(d, eh, bh, idesc, true);
+              mma_bf16(d, eh, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(rel);
+            }
+          }
+        }
+        TR(102);
+        if (elect_one()) mma_commit(acc_done);
+        // ---- GEMM2 (-> acc0), GEMM3 (-> acc0), GEMM4a (-> acc1), GEMM4b (acc1 +=) ----
+        for (int gi = 1; gi < 5; ++gi) {
+          TR(100 + 10 * gi);
+          wait_operand();
+          TR(101 + 10 * gi);
+          const uint32_t d = tmem_base + (gi >= 3 ? C::ACC1_COL : 0);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            uint64_t bh, *rel;
+            take_slot(bh, rel);
+            if (elect_one()) {
+              const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+              mma_bf16(d, ah, bh, idesc, gi == 4 || ks > 0);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(rel);
+            }
+          }
+          TR(102 + 10 * gi);
+          if (elect_one()) mma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int ww = warp - 2;
+    const int wtid = tid - 64;
+    const int quarter = warp & 3;
+    const int part = ww >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t done_phase = 0;
+#ifdef NSDP_TRACE
+    const bool tr_on = (tid == 64);
+#define TW(id) do { if (tr_on) TR(id); } while (0)
+#else
+#define TW(id) do { } while (0)
+#endif
+    constexpr int NQ = (C::CHUNKS + C::NPART - 1) / C::NPART;           // chunk rounds per thread (chunk = part + q*NPART)
+    constexpr int NE = (C::E_COLS / 8 + C::NPART - 1) / C::NPART;
+    static_assert(NQ * 8 <= 64, "ReLU mask of G is kept in one 64-bit register");
+    const int slabs = stg.lo ? 2 : 1;
+    const uint32_t a_base = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);                         // + chunk * 2048
+    const size_t st_row = (size_t)(r >> 4) * (size_t)(slabs * C::DP * 32) + (size_t)(r & 15) * 16;   // + chunk * 256
+    const size_t st_tile = (size_t)slabs * 256 * C::DP;
+    const size_t ste_row = (size_t)(r >> 4) * (size_t)(C::E_COLS * 32) + (size_t)(r & 15) * 16;
+    float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cb = 0.f;   // d_wd0 / d_bd0 of column wtid, accumulated over all tiles
+
+    auto wait_acc = [&]() {
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+    };
+    auto publish = [&]() {
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    };
+    // x[8] -> bf16 hi/lo words; optional A operand store, optional staged store
+    auto emit = [&](const float (&x)[8], int ch, bool to_a, unsigned char *stage_tile, uint4 &hi, uint4 &lo) {
+      split2(x[0], x[1], hi.x, lo.x);
+      split2(x[2], x[3], hi.y, lo.y);
+      split2(x[4], x[5], hi.z, lo.z);
+      split2(x[6], x[7], hi.w, lo.w);
+      if (to_a) {
+        *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = hi;
+        *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = lo;
+      }
+      if (stage_tile) {
+        unsigned char *p = stage_tile + st_row + (size_t)ch * 256;
+        *reinterpret_cast<uint4 *>(p) = hi;
+        if (stg.lo) *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+      }
+    };
+
+    RowInfoPB ri = row_info_pb<C>(a, tile_begin + blockIdx.x, r, krows, tpb);
+    for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      TW(200);
+      const size_t tl = (size_t)(tile - tile_begin);
+      const bool row_on = ri.c >= 0;
+      const int b = (int)(tile / tpb);
+      if (part == 0) rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
+      unsigned long long gmaskbits = 0ull;
+      // ---- operands H (A + staged) and E (smem + staged) -----------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w0 = wd0s[ch * 8 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
+          }
+          uint4 hi, lo;
+          emit(h, ch, true, stg.h + tl * st_tile, hi, lo);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::E_COLS / 8) {
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if ((ri.j >> 3) == ch) {
+            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;
+            const int w = (ri.j & 7) >> 1;
+            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(E + a_base + ch * 2048) = e;
+          *reinterpret_cast<uint4 *>(stg.e + tl * (size_t)(256 * C::E_COLS) + ste_row + (size_t)ch * 256) = e;
+        }
+      }
+      publish();
+      TW(201);
+      // ---- G = relu(acc0 + pc): operand, staged, mask -------------------------------------------------------------
+      wait_acc();
+      TW(202);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          float v[8], gg[8];
+          tmem_ld8(trow + ch * 8, v);
+          const float4 p0 = *reinterpret_cast<const float4 *>(pcs + ch * 8), p1 = *reinterpret_cast<const float4 *>(pcs + ch * 8 + 4);
+          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gg[j] = fmaxf(v[j] + pv[j], 0.f);
+            if (gg[j] > 0.f) gmaskbits |= 1ull << (q * 8 + j);
+          }
+          uint4 hi, lo;
+          emit(gg, ch, true, stg.g + tl * st_tile, hi, lo);
+        }
+      }
+      publish();
+      TW(203);
+      // ---- while GEMM2 runs: the next tile's row description -------------------------------------------------------------
+      const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
+      // ---- w = exp(a - max) / sum, s = acc1 + vc; ds = w * dout, da = ds * (s - out) ---------------------------------------
+      //      da -> A operand + staged; ds -> staged + parked (split words) in acc1's columns
+      {
+        const float *st_mx = stats + (size_t)(row_on ? ri.c : 0) * D;
+        const float *st_iv = stats + ((size_t)BM + (row_on ? ri.c : 0)) * D;
+        const float *p_go = dout + (size_t)(row_on ? ri.c : 0) * D;
+        const float *p_o = out + (size_t)(row_on ? ri.c : 0) * D;
+        float4 cmx, civ, cgo, co;   // inputs of the current half-chunk (loaded one half-chunk ahead)
+        auto load_half = [&](int hc, float4 &mx, float4 &iv, float4 &go, float4 &o) {
+          const int col = (part + (hc >> 1) * C::NPART) * 8 + (hc & 1) * 4;
+          mx = iv = go = o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_on && col < D) {
+            mx = ldg4(st_mx + col); iv = ldg4(st_iv + col); go = ldg4(p_go + col); o = ldg4(p_o + col);
+          }
+        };
+        load_half(0, cmx, civ, cgo, co);
+        wait_acc();
+      TW(204);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          float av[8], sv[8], ds[8], da[8];
+          if (ch < C::CHUNKS) {
+            tmem_ld8(trow + ch * 8, av);
+            tmem_ld8(trow + C::ACC1_COL + ch * 8, sv);
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 nmx, niv, ngo, no;
+            load_half(q * 2 + half + 1, nmx, niv, ngo, no);   // beyond the last chunk: col >= D, nothing is loaded
+            if (ch < C::CHUNKS) {
+              const float4 v0 = *reinterpret_cast<const float4 *>(vcs + ch * 8 + half * 4);
+              const float mxs[4] = {cmx.x, cmx.y, cmx.z, cmx.w}, ivs[4] = {civ.x, civ.y, civ.z, civ.w};
+              const float gos[4] = {cgo.x, cgo.y, cgo.z, cgo.w}, os[4] = {co.x, co.y, co.z, co.w};
+              const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
+              const bool on = row_on && ch * 8 + half * 4 < D;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = half * 4 + u;
+                const float w = on ? __expf(av[j] - mxs[u]) * ivs[u] : 0.f;
+                ds[j] = w * gos[u];
+                da[j] = ds[j] * (sv[j] + vv[u] - os[u]);
+              }
+            }
+            cmx = nmx; civ = niv; cgo = ngo; co = no;
+          }
+          if (ch < C::CHUNKS) {
+            uint4 hi, lo;
+            emit(da, ch, true, stg.da + tl * st_tile, hi, lo);
+            emit(ds, ch, false, stg.ds + tl * st_tile, hi, lo);
+            const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
+            tmem_st8(trow + C::ACC1_COL + ch * 8, pk);
+          }
+        }
+      }
+      tmem_st_wait();
+      publish();
+      TW(205);
+      // ---- GEMM3 done: A is free -> operand ds from its parked words (GEMM4a) ---------------------------------------------
+      wait_acc();
+      TW(206);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          uint32_t pk[8];
+          tmem_ld8u(trow + C::ACC1_COL + ch * 8, pk);
+          *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      publish();
+      TW(207);
+      // ---- dgp = dg * [g > 0] (reads acc0 while GEMM4a fills acc1): staged + parked in acc0's columns ---------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          float dg[8];
+          tmem_ld8(trow + ch * 8, dg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dg[j] = ((gmaskbits >> (q * 8 + j)) & 1ull) ? dg[j] : 0.f;
+          uint4 hi, lo;
+          emit(dg, ch, false, stg.dgp + tl * st_tile, hi, lo);
+          const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
+          tmem_st8(trow + ch * 8, pk);
+        }
+      }
+      tmem_st_wait();
+      TW(208);
+      // ---- GEMM4a done: A is free -> operand dgp (GEMM4b) ----------------------------------------------------------------------
+      wait_acc();
+      TW(209);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          uint32_t pk[8];
+          tmem_ld8u(trow + ch * 8, pk);
+          *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      publish();
+      TW(210);
+      // ---- dpre = dh * [h > 0]; d rel; dpre -> fp32 scratch (aliases A, free once GEMM4b is done) ------------------------------
+      wait_acc();
+      TW(211);
+      {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            float dh[8];
+            tmem_ld8(trow + C::ACC1_COL + ch * 8, dh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = ch * 8 + j;
+              const float4 w0 = wd0s[col];
+              const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+              const float dp = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
+              sx = fmaf(dp, w0.x, sx); sy = fmaf(dp, w0.y, sy); sz = fmaf(dp, w0.z, sz);
+              if (col < D) scratch[(size_t)col * L::SCR_LD + ((r + col) & 127)] = dp;
+            }
+          }
+        }
+        relacc[(part * 3 + 0) * 128 + r] = sx;
+        relacc[(part * 3 + 1) * 128 + r] = sy;
+        relacc[(part * 3 + 2) * 128 + r] = sz;
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
+      TW(212);
+      if (wtid < D) {   // column owners: d_wd0 / d_bd0 partial sums over the 128 rows of the tile
+        const float *colp = scratch + (size_t)wtid * L::SCR_LD;
+#pragma unroll 4
+        for (int rr = 0; rr < 128; ++rr) {
+          const float dp = colp[(rr + wtid) & 127];
+          const float4 rl = rels[rr];
+          cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
+        }
+      }
+      if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {   // row owners: d_xyz
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < C::NPART; ++pp) {
+          sx += relacc[(pp * 3 + 0) * 128 + r];
+          sy += relacc[(pp * 3 + 1) * 128 + r];
+          sz += relacc[(pp * 3 + 2) * 128 + r];
+        }
+        if (g.d_xyz_c) {
+          float *dst = g.d_xyz_c + (size_t)ri.c * 3;
+          atomicAdd(dst, a.sign * sx); atomicAdd(dst + 1, a.sign * sy); atomicAdd(dst + 2, a.sign * sz);
+        }
+        if (g.d_xyz_n) {
+          float *dst = g.d_xyz_n + ((size_t)b * a.N + ri.j) * 3;
+          atomicAdd(dst, -a.sign * sx); atomicAdd(dst + 1, -a.sign * sy); atomicAdd(dst + 2, -a.sign * sz);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
+      TW(213);
+      ri = nxt;
+    }
+    if (wtid < D) {
+      if (g.d_wd0) {
+        atomicAdd(g.d_wd0 + wtid * 3 + 0, cw0); atomicAdd(g.d_wd0 + wtid * 3 + 1, cw1); atomicAdd(g.d_wd0 + wtid * 3 + 2, cw2);
+      }
+      if (g.d_bd0) atomicAdd(g.d_bd0 + wtid, cb);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// dT1 / dT2 [B][E_COLS][D] (rows <= N valid) -> d_kp, d_gq, d_pc / d_vp, d_gv, d_vc (see the table definitions in
+// vattn_fwd_oh_kernel): one thread per (shape, column)
+template <class C>
+__global__ void finalize_tables_kernel(const float *__restrict__ dt1, const float *__restrict__ dt2, const nsdp_vattn_grads g,
+                                       int B, int N, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, c = i - b * D;
+  const float *t1 = dt1 + (size_t)b * C::E_COLS * D + c, *t2 = dt2 + (size_t)b * C::E_COLS * D + c;
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = 0; j < N; ++j) {
+    const float x1 = t1[(size_t)j * D], x2 = t2[(size_t)j * D];
+    s1 += x1; s2 += x2;
+    if (g.d_kp) g.d_kp[((size_t)b * N + j) * D + c] -= x1;
+    if (g.d_vp) g.d_vp[((size_t)b * N + j) * D + c] += x2;
+  }
+  if (g.d_gq) g.d_gq[(size_t)b * D + c] += t1[(size_t)N * D];
+  if (g.d_gv) g.d_gv[(size_t)b * D + c] += t2[(size_t)N * D];
+  if (g.d_pc) atomicAdd(g.d_pc + c, s1);
+  if (g.d_vc) atomicAdd(g.d_vc + c, s2);
+}
+
+// rows above which the weight / table gradient reductions use plain bf16 operand tiles (hi half only): the rounding errors
+// of millions of independent rows average out (measured against the fp32 reference in tests/test_gpu_vattn.py), and the
+// staged traffic halves. NSDP_STAGE_LO=1 forces fp32-grade staging everywhere.
+static bool stage_lo_for(long long pair_rows) {
+  static const int forced = [] { const char *e = getenv("NSDP_STAGE_LO"); return e ? atoi(e) : -1; }();
+  if (forced >= 0) return forced != 0;
+  return pair_rows < (1ll << 20);
+}
+
+template <class C>
+static size_t bwd_oh_workspace_bytes(const nsdp_vattn_args &a) {
+  const int tpb = (a.M + C::CENTRES - 1) / C::CENTRES;
+  const long long tiles = (long long)a.B * tpb;
+  const long long seg = tiles < kSegmentTiles ? tiles : kSegmentTiles;
+  const size_t slabs = stage_lo_for(tiles * 128) ? 2 : 1;
+  return bwd_packed_bytes<C>() + (size_t)a.B * table_bytes_per_shape<C>() + 256 +
+         2 * sizeof(float) * (size_t)a.B * C::E_COLS * a.D + (size_t)seg * (5 * slabs * 256 * C::DP + 256 * C::E_COLS);
+}
+
+template <class C>
+static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float *stats, const float *dout,
+                         const nsdp_vattn_grads &g, void *workspace, size_t ws_bytes, cudaStream_t st) {
+  if (!workspace || ws_bytes < bwd_oh_workspace_bytes<C>(a)) return NSDP_ERR_WORKSPACE;
+  if (!g.d_wd2t || !g.d_wpt || !g.d_wg2t) return NSDP_ERR_INVALID_ARGUMENT;
+  const int tpb = (a.M + C::CENTRES - 1) / C::CENTRES;
+  const long long tiles = (long long)a.B * tpb;
+  const long long seg = tiles < kSegmentTiles ? tiles : kSegmentTiles;
+  const int lo = stage_lo_for(tiles * 128) ? 1 : 0;
+  const size_t slabs = lo ? 2 : 1;
+  unsigned char *packed = (unsigned char *)workspace;
+  unsigned char *tables = packed + bwd_packed_bytes<C>();
+  int *err = (int *)(tables + (size_t)a.B * table_bytes_per_shape<C>());
+  float *dt1 = (float *)((unsigned char *)err + 256);
+  const size_t tbl = (size_t)a.B * C::E_COLS * a.D;
+  float *dt2 = dt1 + tbl;
+  unsigned char *sbase = (unsigned char *)(dt2 + tbl);
+  const size_t per = (size_t)seg * slabs * 256 * C::DP;
+  OhStaging stg{sbase, sbase + per, sbase + 2 * per, sbase + 3 * per, sbase + 4 * per, sbase + 5 * per, lo};
+  cudaError_t e = cudaMemsetAsync(err, 0, 256 + 2 * tbl * sizeof(float), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  pack_bwd_weights_kernel<C><<<96, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
+  int rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables);
+  rc = check_launch();
+  if (rc != NSDP_OK) return rc;
+  auto kern = vattn_bwd_oh_kernel<C>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<C>::SMEM);
+  if (e != cudaSuccess) return cuda_rc(e);
+  for (long long t0 = 0; t0 < tiles; t0 += seg) {
+    const long long t1 = t0 + seg < tiles ? t0 + seg : tiles;
+    const long long n = t1 - t0;
+    const int grid = (int)(n < num_sms() ? n : num_sms());
+    unsigned long long *trace = nullptr;
+#ifdef NSDP_TRACE
+    if (const char *tp = getenv("NSDP_TRACE_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
+#endif
+    kern<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, g, packed, tables, stg, tpb, t0, t1, err, trace);
+    rc = check_launch();
+    if (rc != NSDP_OK) return rc;
+    // weight gradients over the whole segment + table gradients per shape (tile ranges relative to the segment)
+    dwtc::Job jobs[dwtc_max_jobs];
+    int nj = 0;
+    auto flush = [&]() -> int {
+      const int r2 = nj ? dw_tc_launch(jobs, nj, n, err, st) : NSDP_OK;
+      nj = 0;
+      return r2;
+    };
+    auto wjob = [&](const unsigned char *x, const unsigned char *y, float *o) {
+      dwtc::Job j{x, y, o, C::DP, C::DP, a.D, a.D, a.D, nullptr, nullptr, 0, 0, 0};
+      j.x_lo = lo; j.y_lo = lo;
+      return j;
+    };
+    jobs[nj++] = wjob(stg.g, stg.da, g.d_wg2t);
+    jobs[nj++] = wjob(stg.h, stg.dgp, g.d_wpt);
+    jobs[nj++] = wjob(stg.h, stg.ds, g.d_wd2t);
+    for (long long b = t0 / tpb; b * tpb < t1; ++b) {
+      const long long r0 = (b * tpb > t0 ? b * tpb : t0) - t0, r1 = ((b + 1) * tpb < t1 ? (b + 1) * tpb : t1) - t0;
+      for (int m = 0; m < 2; ++m) {
+        if (nj == dwtc_max_jobs) {
+          rc = flush();
+          if (rc != NSDP_OK) return rc;
+        }
+        dwtc::Job j{stg.e, m == 0 ? stg.dgp : stg.ds, (m == 0 ? dt1 : dt2) + (size_t)b * C::E_COLS * a.D, C::E_COLS, C::DP,
+                    a.N + 1, a.D, a.D, nullptr, nullptr, 0, 0, 0};
+        j.x_lo = 0; j.y_lo = lo; j.t0 = r0; j.t1 = r1;
+        jobs[nj++] = j;
+      }
+    }
+    rc = flush();
+    if (rc != NSDP_OK) return rc;
+  }
+  finalize_tables_kernel<C><<<(unsigned)ceil_div(a.B * a.D, 128), 128, 0, st>>>(dt1, dt2, g, a.B, a.N, a.D);
+  return check_launch();
+}
+
+static bool bwd_oh_ok(const nsdp_vattn_args &a) {
+  static const bool off = [] { const char *e = getenv("NSDP_NO_ONEHOT"); return e && atoi(e) != 0; }();
+  return !off && a.has_global && !a.qp && a.kp && a.vp && a.gq && a.gv && a.idx && a.N + 1 <= 112 && a.K + 1 <= 8 && a.M >= 16;
+}
+
 static int pick_bwd(const nsdp_vattn_args &a) {
   const int krows = a.K + (a.has_global ? 1 : 0);
   if (a.D % 4 != 0 || a.D > 256 || !a.kp || !a.vp) return 0;
@@ -597,7 +1214,9 @@ constexpr int BWD_NPART = NSDP_BWD_NPART;  // worker warps per TMEM lane quarter
 
 size_t vattn_bwd_tc_workspace_bytes(const nsdp_vattn_args *a) {
   switch (vtc::pick_bwd(*a)) {
-    case 1: return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8, BWD_NPART>>(*a);
+    case 1:
+      if (vtc::bwd_oh_ok(*a)) return vtc::bwd_oh_workspace_bytes<vtc::TcCfg<208, 8, 4, true>>(*a);
+      return vtc::bwd_workspace_bytes<vtc::TcCfg<208, 8, BWD_NPART>>(*a);
     case 2: return vtc::bwd_workspace_bytes<vtc::TcCfg<128, 16, BWD_NPART>>(*a);
     case 3: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 16, BWD_NPART>>(*a);
     case 4: return vtc::bwd_workspace_bytes<vtc::TcCfg<256, 128, BWD_NPART>>(*a);
@@ -609,7 +1228,10 @@ int vattn_bwd_tc_dispatch(const nsdp_vattn_args *a, const float *out, const floa
                           const nsdp_vattn_grads *g, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled) {
   *handled = true;
   switch (vtc::pick_bwd(*a)) {
-    case 1: return vtc::launch_bwd<vtc::TcCfg<208, 8, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+    case 1:
+      if (vtc::bwd_oh_ok(*a))
+        return vtc::launch_bwd_oh<vtc::TcCfg<208, 8, 4, true>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
+      return vtc::launch_bwd<vtc::TcCfg<208, 8, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
     case 2: return vtc::launch_bwd<vtc::TcCfg<128, 16, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
     case 3: return vtc::launch_bwd<vtc::TcCfg<256, 16, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);
     case 4: return vtc::launch_bwd<vtc::TcCfg<256, 128, BWD_NPART>>(*a, out, stats, dout, *g, workspace, ws_bytes, st);

@@ -116,52 +116,55 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
 
   if (warp == 0) {
     // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;   // slot counter
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        // the packed image is consumed front to back: 2 slots per k-step of GEMM1, then 1 slot per k-step of GEMM2
-        const unsigned char *src = packed;
-        for (int j = 0; j < 3 * C::KSTEPS; ++j, ++it, src += C::SLOT_BYTES) {
-          const int s = it % C::SLOTS;
-          const uint32_t ph = (it / C::SLOTS) & 1;
-          mbar_wait(&empty[s], ph ^ 1, err);  // first round passes immediately (fresh barrier, parity trick)
-          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
-          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
-        }
+    // the packed image is consumed front to back once per tile: 2 slots per k-step of GEMM1, then 1 slot per k-step of
+    // GEMM2; PL lanes share the copies (lane l serves slots l, l + PL, ...), see vattn_fwd_oh_kernel
+    constexpr int PL = C::SLOTS / 2;
+    constexpr int PER_TILE = 3 * C::KSTEPS;
+    if (lane < PL) {
+      const long long my_tiles = (long long)blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const long long total = my_tiles * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const int j = (int)(it % PER_TILE);
+        const int s = (int)(it % C::SLOTS);
+        const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);  // first round passes immediately (fresh barrier, parity trick)
+        mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+        bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, packed + (size_t)j * C::SLOT_BYTES, C::SLOT_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp runs loops and waits, one elected lane issues (see vattn_fwd_oh_kernel)
+    {
       const uint32_t idesc = idesc_bf16(128, C::DP);
-      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
-      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo);
-      uint32_t it = 0, ready_phase = 0;
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         for (int g = 0; g < 2; ++g) {
           mbar_wait(a_ready, ready_phase, err);
           ready_phase ^= 1;
           tc_fence_after();
           for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
-            const bool acc = ks > 0;
             // GEMM1: slot 0 = W' -> acc0, slot 1 = Wd2 -> acc1 ; GEMM2: one slot, Wg2 -> acc0
-            for (int m = 0; m < (g == 0 ? 2 : 1); ++m, ++it) {
-              const int s = it % C::SLOTS;
-              const uint32_t ph = (it / C::SLOTS) & 1;
-              mbar_wait(&full[s], ph, err);
+            for (int m = 0; m < (g == 0 ? 2 : 1); ++m) {
+              mbar_wait(&full[slot], slot_phase, err);
               tc_fence_after();
-              const uint32_t sb = smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
-              const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
-              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
-              mma_bf16(d, ah, bh, idesc, acc);
-              mma_bf16(d, al, bh, idesc, true);
-              mma_bf16(d, ah, bl, idesc, true);
-              mma_commit(&empty[s]);
+              if (elect_one()) {
+                const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+                const uint64_t bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
+                const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+                mma_bf16(d, ah, bh, idesc, ks > 0);
+                mma_bf16(d, al, bh, idesc, true);
+                mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+                mma_commit(&empty[slot]);
+              }
+              if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
             }
           }
-          mma_commit(acc_done);
+          if (elect_one()) mma_commit(acc_done);
         }
       }
     }
@@ -422,45 +425,6 @@ vattn_fwd_tc_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
 // shape b are pre-packed like the weights and stream through the same slot ring. E is exact in bf16: 2 MMAs per k-step.
 // =====================================================================================================================
 template <class C>
-constexpr size_t table_bytes_per_shape() {
-  return (size_t)C::E_KSTEPS * 2 * C::SLOT_BYTES;   // per k-step: [T1 hi][T1 lo][T2 hi][T2 lo]
-}
-
-template <class C>
-__global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__restrict__ out) {
-  // one thread per (shape b, table m, column n, anchor pair k)
-  const int per = C::DP * (C::E_COLS / 2);
-  const long long total = (long long)a.B * 2 * per;
-  const int D = a.D, N = a.N;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(e / (2 * per));
-    const int rem0 = (int)(e - (long long)b * 2 * per);
-    const int m = rem0 / per, rem = rem0 - m * per;
-    const int n = rem / (C::E_COLS / 2), k = (rem - n * (C::E_COLS / 2)) * 2;
-    float x[2] = {0.f, 0.f};
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = k + u;
-      if (n < D) {
-        if (j < N) {
-          const size_t off = ((size_t)b * N + j) * D + n;
-          x[u] = m == 0 ? -a.kp[off] : a.vp[off];
-        } else if (j == N) {
-          x[u] = m == 0 ? a.gq[(size_t)b * D + n] - a.pc[n] : a.gv[(size_t)b * D + n] - a.vc[n];
-        }
-      }
-    }
-    uint32_t hi, lo;
-    split2(x[0], x[1], hi, lo);
-    const int ks = k >> 4;
-    unsigned char *base = out + (size_t)b * table_bytes_per_shape<C>() + (size_t)(ks * 2 + m) * C::SLOT_BYTES;
-    const uint32_t in_slab = canon_off(C::DP, n, k & 15);
-    *reinterpret_cast<uint32_t *>(base + in_slab) = hi;
-    *reinterpret_cast<uint32_t *>(base + C::SLAB + in_slab) = lo;
-  }
-}
-
-template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
 vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed,
                     const unsigned char *__restrict__ tables, float *__restrict__ out, float *__restrict__ stats,
@@ -513,79 +477,97 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
 
   if (warp == 0) {
     // ===================== producer: weights + this shape's tables, one slot at a time =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // PL lanes share the work (lane l serves slots l, l + PL, ...): a single thread sustains only about one bulk copy
+    // per ~500 cycles (serial wait / expect_tx / issue chain), less than the tensor pipe consumes
+    constexpr int PL = C::SLOTS / 2;
+    constexpr int PER_TILE = W1 + T1 + C::KSTEPS;
+    if (lane < PL) {
+      const long long my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+      const long long total = my_tiles * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const long long tile = blockIdx.x + (it / PER_TILE) * gridDim.x;
+        const int j = (int)(it % PER_TILE);
         const unsigned char *tb = tables + (size_t)(tile / tpb) * table_bytes_per_shape<C>();
-        for (int j = 0; j < W1 + T1 + C::KSTEPS; ++j, ++it) {
-          const unsigned char *src = j < W1 ? packed + (size_t)j * C::SLOT_BYTES
-                                            : (j < W1 + T1 ? tb + (size_t)(j - W1) * C::SLOT_BYTES
-                                                           : packed + (size_t)(j - T1) * C::SLOT_BYTES);
-          const int s = it % C::SLOTS;
-          const uint32_t ph = (it / C::SLOTS) & 1;
-          mbar_wait(&empty[s], ph ^ 1, err);
-          mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
-          bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
-        }
+        const unsigned char *src = j < W1 ? packed + (size_t)j * C::SLOT_BYTES
+                                          : (j < W1 + T1 ? tb + (size_t)(j - W1) * C::SLOT_BYTES
+                                                         : packed + (size_t)(j - T1) * C::SLOT_BYTES);
+        const int s = (int)(it % C::SLOTS);
+        const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+        bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, src, C::SLOT_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loops and the waits; one elected lane issues (elect_one: straight UTCHMMA issue instead of a
+    // per-lane loop). The issuing thread must stay under the ~310 cycles the tensor pipe needs for three MMAs per slot:
+    // descriptors advance by adds (the start-address field counts 16-byte units), the ring position is a running counter.
+    {
       const uint32_t idesc = idesc_bf16(128, C::DP);
-      const uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
-      const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo), e_addr = smem_u32(E);
-      uint32_t it = 0, ready_phase = 0;
-      auto next_slot = [&]() -> uint32_t {   // waits for the next slot of the ring, returns its shared address
-        const int s = it % C::SLOTS;
-        const uint32_t ph = (it / C::SLOTS) & 1;
-        mbar_wait(&full[s], ph, err);
-        tc_fence_after();
-        return smem_u32(stage0 + (size_t)s * C::SLOT_BYTES);
-      };
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+      auto wait_operand = [&]() {
         mbar_wait(a_ready, ready_phase, err);
         ready_phase ^= 1;
         tc_fence_after();
+      };
+      auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
+        mbar_wait(&full[slot], slot_phase, err);
+        tc_fence_after();
+        bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
+        release = &empty[slot];
+        if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
+      };
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        wait_operand();
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
-          const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
-          for (int m = 0; m < 2; ++m, ++it) {
-            const uint32_t sb = next_slot();
-            const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
-            const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
-            mma_bf16(d, ah, bh, idesc, ks > 0);
-            mma_bf16(d, al, bh, idesc, true);
-            mma_bf16(d, ah, bl, idesc, true);
-            mma_commit(&empty[it % C::SLOTS]);
+          const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint64_t bh, *rel;
+            take_slot(bh, rel);
+            if (elect_one()) {
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+              mma_bf16(d, ah, bh, idesc, ks > 0);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(rel);
+            }
           }
         }
         for (int ks = 0; ks < C::E_KSTEPS; ++ks) {
-          const uint64_t eh = smem_desc(e_addr + ks * 2 * lbo_a, lbo_a, 128);
-          for (int m = 0; m < 2; ++m, ++it) {
-            const uint32_t sb = next_slot();
-            const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
-            const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
-            mma_bf16(d, eh, bh, idesc, true);
-            mma_bf16(d, eh, bl, idesc, true);
-            mma_commit(&empty[it % C::SLOTS]);
+          const uint64_t eh = eh0 + ks * A_STEP;
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint64_t bh, *rel;
+            take_slot(bh, rel);
+            if (elect_one()) {
+              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
+              mma_bf16(d, eh, bh, idesc, true);
+              mma_bf16(d, eh, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(rel);
+            }
           }
         }
-        mma_commit(acc_done);
-        mbar_wait(a_ready, ready_phase, err);
-        ready_phase ^= 1;
-        tc_fence_after();
-        for (int ks = 0; ks < C::KSTEPS; ++ks, ++it) {
-          const uint64_t ah = smem_desc(a_hi_addr + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t al = smem_desc(a_lo_addr + ks * 2 * lbo_a, lbo_a, 128);
-          const uint32_t sb = next_slot();
-          const uint64_t bh = smem_desc(sb, lbo_b, 128), bl = smem_desc(sb + C::SLAB, lbo_b, 128);
-          mma_bf16(tmem_base, ah, bh, idesc, ks > 0);
-          mma_bf16(tmem_base, al, bh, idesc, true);
-          mma_bf16(tmem_base, ah, bl, idesc, true);
-          mma_commit(&empty[it % C::SLOTS]);
+        if (elect_one()) mma_commit(acc_done);
+        wait_operand();
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          uint64_t bh, *rel;
+          take_slot(bh, rel);
+          if (elect_one()) {
+            const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+            mma_bf16(tmem_base, ah, bh, idesc, ks > 0);
+            mma_bf16(tmem_base, al, bh, idesc, true);
+            mma_bf16(tmem_base, ah, bh + (C::SLAB >> 4), idesc, true);
+            mma_commit(rel);
+          }
         }
-        mma_commit(acc_done);
+        if (elect_one()) mma_commit(acc_done);
       }
     }
   } else {

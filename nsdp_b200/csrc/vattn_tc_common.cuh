@@ -206,6 +206,46 @@ __device__ __forceinline__ float group_transpose_max(float (&v)[8], int lane) {
   return v[0];
 }
 
+// ---- per-shape anchor tables of the OH kernels (see vattn_fwd_oh_kernel), packed like the weights ------------------------
+template <class C>
+constexpr size_t table_bytes_per_shape() {
+  return (size_t)C::E_KSTEPS * 2 * C::SLOT_BYTES;   // per k-step: [T1 hi][T1 lo][T2 hi][T2 lo]
+}
+
+template <class C>
+__global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__restrict__ out) {
+  // one thread per (shape b, table m, column n, anchor pair k)
+  const int per = C::DP * (C::E_COLS / 2);
+  const long long total = (long long)a.B * 2 * per;
+  const int D = a.D, N = a.N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / (2 * per));
+    const int rem0 = (int)(e - (long long)b * 2 * per);
+    const int m = rem0 / per, rem = rem0 - m * per;
+    const int n = rem / (C::E_COLS / 2), k = (rem - n * (C::E_COLS / 2)) * 2;
+    float x[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = k + u;
+      if (n < D) {
+        if (j < N) {
+          const size_t off = ((size_t)b * N + j) * D + n;
+          x[u] = m == 0 ? -a.kp[off] : a.vp[off];
+        } else if (j == N) {
+          x[u] = m == 0 ? a.gq[(size_t)b * D + n] - a.pc[n] : a.gv[(size_t)b * D + n] - a.vc[n];
+        }
+      }
+    }
+    uint32_t hi, lo;
+    split2(x[0], x[1], hi, lo);
+    const int ks = k >> 4;
+    unsigned char *base = out + (size_t)b * table_bytes_per_shape<C>() + (size_t)(ks * 2 + m) * C::SLOT_BYTES;
+    const uint32_t in_slab = canon_off(C::DP, n, k & 15);
+    *reinterpret_cast<uint32_t *>(base + in_slab) = hi;
+    *reinterpret_cast<uint32_t *>(base + C::SLAB + in_slab) = lo;
+  }
+}
+
 __device__ __forceinline__ int float_order_key(float x) {
   const int i = __float_as_int(x);
   return i ^ ((i >> 31) & 0x7fffffff);
