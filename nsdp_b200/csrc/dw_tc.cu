@@ -30,6 +30,7 @@ struct Params {
   int njobs;
   int cta_begin[MAX_JOBS + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split the tile range of job j
   int stages;              // ring depth (<= MAX_STAGES)
+  uint32_t ones_off;       // offset of the constant one-hot operand (column sums by MMA) inside dynamic shared memory
   int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
   int *err;
 };
@@ -52,6 +53,23 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   const uint32_t xb = x_lo ? 2 * xs : xs, yb = y_lo ? 2 * ys : ys;
   const uint32_t stage_bytes = xb + yb;
   const int mtiles = job.wx > 128 ? 2 : 1;
+  // Column sums (bias gradients) by the tensor core: colsum[n] = sum_r ONES[r][0] * Y[r][n] with the constant operand
+  // ONES[r][m] = (m == 0), accumulated in a spare TMEM region whose row 0 is flushed at the end. The warp-level path
+  // below only remains for the per-batch sums (gsum) and for shapes without a spare region.
+  const int cs_col = job.wy <= 128 ? 128 : (mtiles == 1 ? 256 : -1);
+  const bool mma_cs = job.colsum != nullptr && job.gsum == nullptr && cs_col >= 0;
+  unsigned char *ones = smem + p.ones_off;
+  if (warp >= 2) {
+    const int t = tid - 64;   // 128 threads x 32 bytes
+    *reinterpret_cast<uint4 *>(ones + t * 32) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(ones + t * 32 + 16) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    if (t < 8) {   // rows 2t, 2t+1 of column group 0: element (r, 0) = bf16 1.0
+      *reinterpret_cast<uint32_t *>(ones + t * 32) = 0x00003F80u;
+      *reinterpret_cast<uint32_t *>(ones + t * 32 + 16) = 0x00003F80u;
+    }
+    fence_async_smem();
+  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -92,6 +110,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
     if (has_work) {
       const uint32_t idesc = idesc_bf16_mn(128, job.wy);
       const uint64_t x0 = smem_desc(smem_u32(smem), 128, 256);
+      const uint64_t ones_desc = smem_desc(smem_u32(ones), 128, 256);
       const uint32_t stage16 = stage_bytes >> 4;
       uint32_t slot = 0, slot_phase = 0;
       bool first = true;
@@ -110,6 +129,10 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
             if (x_lo) mma_bf16(d, xl, yh, idesc, true);
             if (y_lo) mma_bf16(d, xh, yl, idesc, true);
           }
+          if (mma_cs) {
+            mma_bf16(tmem_base + cs_col, ones_desc, yh, idesc, !first);
+            if (y_lo) mma_bf16(tmem_base + cs_col, ones_desc, yl, idesc, true);
+          }
           mma_commit(&empty[slot]);
         }
         first = false;
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int gb = -1;   // batch the running gs[] belongs to
       const bool mine = lane * 8 < job.wy;
-      const bool want_cs = job.colsum != nullptr, want_gs = job.gsum != nullptr;
+      const bool want_cs = job.colsum != nullptr && !mma_cs, want_gs = job.gsum != nullptr;
       const unsigned kr_mask = want_gs ? (unsigned)job.g_kr - 1u : 0u;
       const int kr_shift = want_gs ? 31 - __clz(job.g_kr) : 0;
       auto flush_gs = [&]() {
@@ -208,6 +231,17 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
         }
       }
     }
+    if (mma_cs && quarter == 0) {   // row 0 of the column-sum accumulator
+      for (int n0 = 0; n0 < job.wy; n0 += 8) {
+        float v[8];
+        tmem_ld8(trow + cs_col + n0, v);
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (n0 + u < job.nv) atomicAdd(job.colsum + n0 + u, v[u]);
+        }
+      }
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -243,7 +277,7 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
     // bytes one k-step brings into shared memory (the reduction is bandwidth-bound: CTAs are dealt out by bytes)
     const size_t stage = (size_t)32 * (j.wx * ((j.x_lo && p.terms >= 2) ? 2 : 1) + j.wy * ((j.y_lo && p.terms >= 3) ? 2 : 1));
     max_stage = stage > max_stage ? stage : max_stage;
-    cost[i] = (double)stage * (double)(j.t1 - j.t0);
+    cost[i] = (double)(stage + 8192) * (double)(j.t1 - j.t0);   // + a fixed per-k-step share (handoffs, MMA issue)
     total += cost[i];
   }
   p.njobs = njobs;
@@ -262,13 +296,14 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   p.err = err;
   // The ring is as deep as shared memory allows (+ slack for the M-tile-1 overrun): the operand tiles stream from HBM
   // (several microseconds of latency under load), 4 stages left the SMs waiting
-  int stages = (int)((227 * 1024 - 4096 - 1024) / max_stage);
+  int stages = (int)((227 * 1024 - 2 * 4096 - 1024) / max_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return NSDP_ERR_UNSUPPORTED;
   static const int forced = [] { const char *e = getenv("NSDP_DW_STAGES"); return e ? atoi(e) : 0; }();
   if (forced >= 2 && forced < stages) stages = forced;
   p.stages = stages;
-  const size_t smem = (size_t)stages * max_stage + 4096;
+  p.ones_off = (uint32_t)((size_t)stages * max_stage + 4096);
+  const size_t smem = (size_t)stages * max_stage + 2 * 4096;
   cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
   dw_tc_kernel<<<ctas, THREADS, smem, st>>>(p);
