@@ -9,6 +9,8 @@
 //     dlat += dnet*Wc_0                                   (d_lat accumulates in TMEM over the six products)
 // Weight / bias gradients: the operand tiles lat, x_i, y_i, dhh_i, dn_i and dout are staged (bf16 hi/lo, layout of
 // dw_tc.cu) and reduced by dw_tc_kernel (d_w = X^T Y, d_b = column sums of Y).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dw_tc.cuh"
 #include "umma.cuh"
@@ -135,13 +137,14 @@ struct Staging {
   unsigned char *dhh[MAXB];
   unsigned char *dn[MAXB + 1];     // dn[i] = d n_i (i < n), dn[n] = d net_n
   unsigned char *dout;             // width 16
+  int lo;                          // 1: [hi slab][lo slab] per k-step (fp32-grade), 0: hi slab only (plain bf16 operand tiles)
 };
 
 template <int W>
-__device__ __forceinline__ void stage_write(unsigned char *tile, int r, int k0, const uint4 &hi, const uint4 &lo) {
-  unsigned char *p = tile + (size_t)(r >> 4) * (2 * W * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
+__device__ __forceinline__ void stage_write(unsigned char *tile, int r, int k0, const uint4 &hi, const uint4 &lo, int has_lo) {
+  unsigned char *p = tile + (size_t)(r >> 4) * ((has_lo ? 2 : 1) * W * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
   *reinterpret_cast<uint4 *>(p) = hi;
-  *reinterpret_cast<uint4 *>(p + W * 32) = lo;
+  if (has_lo) *reinterpret_cast<uint4 *>(p + W * 32) = lo;
 }
 
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
@@ -341,7 +344,7 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
         const uint32_t off = canon_off(128, r, xb + j);
         *reinterpret_cast<uint4 *>(X_hi + off) = hi;
         *reinterpret_cast<uint4 *>(X_lo + off) = lo;
-        if (stage_tile) stage_write<H>(stage_tile, r, xb + j, hi, lo);
+        if (stage_tile) stage_write<H>(stage_tile, r, xb + j, hi, lo, stg.lo);
       }
     };
     auto load_acc = [&](uint32_t col, float (&v)[XPT]) {
@@ -357,8 +360,9 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
     for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
       const long long grow = tile * 128 + r;
       const bool on = grow < a.R;
-      const size_t toff_h = (size_t)(tile - tile_begin) * 512 * H;
-      const size_t toff_c = (size_t)(tile - tile_begin) * 512 * C::CP;
+      const size_t tstride = stg.lo ? 512 : 256;   // staged bytes per tile and unit of width
+      const size_t toff_h = (size_t)(tile - tile_begin) * tstride * H;
+      const size_t toff_c = (size_t)(tile - tile_begin) * tstride * C::CP;
       uint32_t mx[MAXB + 1], my[MAXB];
       // ---- lat tile -> operand + staging; dout row -> smem + staging ------------------------------------------------------
       {
@@ -374,7 +378,7 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
           const uint32_t off = canon_off(128, r, k0);
           *reinterpret_cast<uint4 *>(L_hi + off) = hi;
           *reinterpret_cast<uint4 *>(L_lo + off) = lo;
-          stage_write<C::CP>(stg.lat + toff_c, r, k0, hi, lo);
+          stage_write<C::CP>(stg.lat + toff_c, r, k0, hi, lo, stg.lo);
         }
         if (part == 0) {
           float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -387,11 +391,11 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
           dos[r] = d;
           const float x0[8] = {d.x, d.y, d.z, d.w, 0.f, 0.f, 0.f, 0.f}, x1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           uint4 hi, lo;
-          unsigned char *dt = stg.dout + (size_t)(tile - tile_begin) * 512 * 16;
+          unsigned char *dt = stg.dout + (size_t)(tile - tile_begin) * tstride * 16;
           split8(x0, hi, lo);
-          stage_write<16>(dt, r, 0, hi, lo);
+          stage_write<16>(dt, r, 0, hi, lo, stg.lo);
           split8(x1, hi, lo);
-          stage_write<16>(dt, r, 8, hi, lo);
+          stage_write<16>(dt, r, 8, hi, lo, stg.lo);
         }
       }
       publish();
@@ -443,7 +447,7 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
           const float x[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
           uint4 hi, lo;
           split8(x, hi, lo);
-          stage_write<H>(stg.x[nb] + toff_h, r, xb + j, hi, lo);
+          stage_write<H>(stg.x[nb] + toff_h, r, xb + j, hi, lo, stg.lo);
         }
       }
       put_x(dnet, stg.dn[nb] + toff_h);
@@ -507,10 +511,15 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
   unsigned char *sbase = packed + packed_bytes<C>(nb) + 256;
   const long long tiles = ceil_div((long long)a.R, 128ll);
   const long long seg = tiles < kSegmentTiles ? tiles : kSegmentTiles;
+  // staging precision of the operand tiles of the weight-gradient reductions: fp32-grade (hi + lo) unless
+  // NSDP_STAGE_LO=0 opts into plain bf16 tiles (see vattn_bwd_tc.cu: stage_lo_for)
+  static const int forced_lo = [] { const char *e = getenv("NSDP_STAGE_LO"); return e ? atoi(e) : 1; }();
+  const int lo = forced_lo != 0;
   Staging stg;
+  stg.lo = lo;
   {
     unsigned char *p = sbase;
-    auto take = [&](int width) { unsigned char *q = p; p += (size_t)seg * 512 * width; return q; };
+    auto take = [&](int width) { unsigned char *q = p; p += (size_t)seg * (lo ? 512 : 256) * width; return q; };
     stg.lat = take(C::CP);
     for (int i = 0; i <= nb; ++i) stg.x[i] = take(H);
     for (int i = 0; i < nb; ++i) stg.y[i] = take(H);
@@ -548,6 +557,7 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     }
     // init_enc: d pre_0 = d net_0 = dn_0 as well
     jobs[nj++] = {stg.lat, stg.dn[0], g.d_wc_t, C::CP, H, a.C, H, wld, g.d_bc, nullptr, 0, 0, 0};
+    for (int j = 0; j < nj; ++j) jobs[j].x_lo = jobs[j].y_lo = lo;
     rc = dw_tc_launch(jobs, nj, n, err, st);
     if (rc != NSDP_OK) return rc;
   }

@@ -385,8 +385,10 @@ vattn_bwd_kernel(const nsdp_vattn_args a, const float *__restrict__ out, const f
   }
   // ---- drel = dpre*Wd0 -> d_xyz_c / d_xyz_n: one warp per row ---------------------------------------------------------
   if (g.d_xyz_c || g.d_xyz_n) {
-    const int warp = tid >> 5, lane = tid & 31, nwarps = (C::THREADS + 31) >> 5;
-    for (int r = warp; r < C::R; r += nwarps) {
+    // only FULL warps take rows: the block size need not be a multiple of 32 (BCfg200 has 500 threads) and the
+    // shuffle reduction below is undefined on a partial warp
+    const int warp = tid >> 5, lane = tid & 31, nwarps = C::THREADS >> 5;
+    for (int r = warp; r < C::R && warp < nwarps; r += nwarps) {
       const RowRef ref = rows[r];
       if (ref.c < 0 || ref.n < 0) continue;  // warp-uniform
       float sx = 0.f, sy = 0.f, sz = 0.f;

@@ -115,7 +115,10 @@ __device__ __forceinline__ RowInfo row_info(const nsdp_vattn_args &a, long long 
   ri.c = -1; ri.n = 0; ri.rx = ri.ry = ri.rz = 0.f; ri.flag = 0.f;
   const int p = r / C::KR, t = r - p * C::KR;
   const long long ci = tile * C::CENTRES + p;
-  if (ci < (long long)a.B * a.M && t < krows) {
+  // neighbours sit in rows 0 .. K-1 of the centre's group, the global token ALWAYS in the last row (KR - 1): the
+  // weight-gradient reduction picks the global rows out of the staged tiles by row % KR == KR - 1
+  (void)krows;
+  if (ci < (long long)a.B * a.M && (t < a.K || (a.has_global && t == C::KR - 1))) {
     const int b = (int)(ci / a.M);
     ri.c = (int)ci;
     if (t < a.K) {

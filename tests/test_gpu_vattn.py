@@ -43,7 +43,7 @@ def vattn_reference(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc
     return (w * val).sum(dim=2)
 
 
-def _rand_case(B, M, N, K, D, pos_only=False, has_global=False, group_all=False, seed=0):
+def _rand_case(B, M, N, K, D, pos_only=False, has_global=False, group_all=False, seed=0, shape_query=False):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     xyz_n = r(B, N, 3) * 0.3
@@ -58,6 +58,8 @@ def _rand_case(B, M, N, K, D, pos_only=False, has_global=False, group_all=False,
     if has_global:
         case["gq"] = r(B, D)
         case["gv"] = r(B, D)
+    if shape_query:   # the decoder as the model calls it: one query vector per SHAPE, folded into kp / gq -> no qp
+        case["qp"] = None
     return case
 
 
@@ -67,6 +69,8 @@ CASES = [
     dict(B=2, M=100, N=100, K=16, D=256),                       # transformer_downs.1
     dict(B=2, M=100, N=100, K=100, D=256, group_all=True),      # full attention over the anchors
     dict(B=2, M=777, N=100, K=7, D=200, has_global=True),       # decoder cross attention
+    dict(B=3, M=777, N=100, K=7, D=200, has_global=True, shape_query=True),   # ... as the model calls it (one-hot kernels)
+    dict(B=2, M=50, N=111, K=5, D=160, has_global=True, shape_query=True),    # widest table, fewer neighbours, D < 200
     dict(B=1, M=129, N=129, K=10, D=120, pos_only=True),        # backward net's first block
     dict(B=1, M=5, N=9, K=3, D=64),                             # odd small
     dict(B=1, M=40, N=40, K=40, D=128, group_all=True),
@@ -126,6 +130,8 @@ BWD_CASES = [
     dict(B=1, M=100, N=100, K=16, D=256),
     dict(B=2, M=100, N=100, K=100, D=256, group_all=True),
     dict(B=2, M=333, N=100, K=7, D=200, has_global=True),
+    dict(B=3, M=333, N=100, K=7, D=200, has_global=True, shape_query=True),   # one-hot chain kernel + table-gradient jobs
+    dict(B=2, M=50, N=111, K=5, D=160, has_global=True, shape_query=True),
     dict(B=1, M=77, N=77, K=10, D=120, pos_only=True),
     dict(B=1, M=9, N=13, K=3, D=64),
 ]
@@ -213,9 +219,10 @@ def test_resnet_tail_backward(R, C, nb, O, impl, monkeypatch):
 # ---------------------------------------------------------------------------------------------------------
 # tcgen05 path (bf16x3 split precision on the tensor cores) vs the fp64 restatement and vs the fp32 CUDA-core kernel
 # ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape_query", [False, True], ids=["per-point-q", "per-shape-q"])
 @pytest.mark.parametrize("M", [16, 777, 5000, 40000])
-def test_vattn_tc_decoder_forward(M, monkeypatch):
-    case = _rand_case(B=2, M=M, N=100, K=7, D=200, has_global=True, seed=M)
+def test_vattn_tc_decoder_forward(M, shape_query, monkeypatch):
+    case = _rand_case(B=2, M=M, N=100, K=7, D=200, has_global=True, seed=M, shape_query=shape_query)
     dev = {k: (v.to(DEV).contiguous() if torch.is_tensor(v) else v) for k, v in case.items()}
     monkeypatch.setattr(ops, "VATTN_IMPL", 2)   # require the tensor-core kernel
     got_tc = ops.vector_attention(sign=1.0, **dev).cpu().double()
@@ -226,6 +233,25 @@ def test_vattn_tc_decoder_forward(M, monkeypatch):
     if M <= 5000:
         want = vattn_reference(sign=1.0, **case)
         assert (got_tc - want).abs().max().item() < 3e-5 * scale
+
+
+def test_vattn_oh_backward_multi_segment(monkeypatch):
+    """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 1250 tiles vs
+    segments of 2048): the one-hot chain kernel + weight / per-shape table gradient jobs against the fp32 CUDA-core
+    backward on the same inputs."""
+    case = _rand_case(B=3, M=20000, N=100, K=7, D=200, has_global=True, seed=21, shape_query=True)
+    names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
+    go = torch.randn(3, 20000, 200, generator=torch.Generator().manual_seed(5)).to(DEV)
+    grads = {}
+    for impl in (1, 2):
+        monkeypatch.setattr(ops, "VATTN_IMPL", impl)
+        dev = {k: (v.to(DEV).contiguous().requires_grad_(True) if k in names else (v.to(DEV) if torch.is_tensor(v) else v))
+               for k, v in case.items()}
+        ops.vector_attention(sign=1.0, **dev).backward(go)
+        grads[impl] = {k: dev[k].grad for k in names}
+    for k in names:
+        ok, info = _tc_grad_ok(k, grads[2][k], grads[1][k])
+        assert ok, (k, info)
 
 
 def test_vattn_tc_stats_feed_backward(monkeypatch):
