@@ -42,6 +42,9 @@ WORKLOAD = "configs[1]: forward-deformation TDNet, batch 8 shapes x 4096 surface
 # (delta MLP 2*3*200 + 2*200*200, gamma MLP 2*2*200*200); the global row is a per-shape constant. Backward = 2x.
 VATTN_DEC_FWD_FLOP_PER_QUERY = 7 * (2 * 3 * 200 + 2 * 200 * 200) + 7 * (2 * 2 * 200 * 200)
 VATTN_DEC_BWD_FLOP_PER_QUERY = 2 * VATTN_DEC_FWD_FLOP_PER_QUERY
+# dram__bytes_read.sum + dram__bytes_write.sum of one decoder-attention backward op (13 chain + 13 reduction launches), from the
+# ncu --set full captures summarised in profiles/ncu_r1_summary.md (None until measured)
+NCU_TRAFFIC_BYTES_PER_OP = None
 
 
 def measured_peaks():
@@ -269,11 +272,24 @@ def run_ours(args):
         bwd_ms = dec_bwd["ms"] / dec_bwd["calls"]
         fwd_ms = dec_fwd["ms"] / dec_fwd["calls"]
         achieved = flops["vattn_bwd"] / (bwd_ms * 1e-3) / 1e12
-        roof = {"kernel": "nsdp_vattn_bwd_f32 for the decoder cross-attention (D=200, 7+1 rows/query): tcgen05 chain kernel "
-                          "vattn_bwd_tc_kernel + split-K weight-gradient kernel dw_tc_kernel, summed per step",
+        # MMA work the op really issues: per 128-row tile the chain kernel runs 6 bf16x3 products of
+        # 128x208x208 (forward recompute + data gradients: 13 k-steps x 3 terms each) + 28 one-hot MMAs, the reduction kernel 3 weight-gradient
+        # products (2 M-tiles x 3 terms) + 2 table-gradient products (2 terms) over 8 k-steps of 16 rows
+        mma = 2 * 128 * 208 * 16
+        tiles = B_PER_GPU * ((N_QUERY + 15) // 16)
+        executed = tiles * mma * ((6 * 13 * 3 + 28) + 8 * (3 * 2 * 3 + 2 * 2))
+        executed_tflops = executed / (bwd_ms * 1e-3) / 1e12
+        roof = {"kernel": "nsdp_vattn_bwd_f32 for the decoder cross-attention (D=200, 7+1 rows/query): tcgen05 one-hot chain "
+                          "kernel vattn_bwd_oh_kernel (13 segment launches) + split-K gradient reduction dw_tc_kernel (weight and "
+                          "per-shape table gradients), timed as one op with CUDA events on the launching stream",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES_PER_OP, "peak_source": peaks["source"],
                 "launch_ms": bwd_ms, "flop_per_launch": flops["vattn_bwd"],
+                "executed_mma_tflops": executed_tflops, "executed_frac": executed_tflops / peaks["bf16_tflops"],
+                "note": "achieved counts ALGORITHMIC flops (SURVEY 8d: 2 x 1.6884 MFLOP per query); the tensor pipe executes "
+                        "~6.9x that (bf16x3 split precision 3x, forward recompute 1.5x, 200->208 padding, one-hot table "
+                        "products), reported as executed_mma_tflops; the reduction kernel streams the staged operand tiles at "
+                        "HBM speed (profiles/)",
                 "share_of_step": dec_bwd["ms"] / prof_steps / prof_step_ms,
                 "top_kernel_by_time": top[0],
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,

@@ -71,6 +71,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
   }
 }
 
+// Polling variant for the single MMA-issuing warp: mbarrier.test_wait never suspends the thread, so the issuer reacts to a
+// finished operand / landed weight slot a few hundred cycles sooner than with try_wait. Only ONE warp per CTA may poll like
+// this: 16+ polling worker warps measurably slow the tensor pipe's shared-memory operand reads down.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity, int *err = nullptr) {
+#ifndef NSDP_ISSUER_POLL   // measured on B200: no gain over try_wait (A/B, bench step 38.5 vs 39.4 ms within noise), so off
+  mbar_wait(bar, parity, err);
+#else
+  if (mbar_test_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u) {
+      const unsigned long long dt = global_ns() - t0;
+      const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
+      if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
+        if (err) atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+#endif
+}
+
 // ---- bulk async copy global -> shared (TMA engine, 1-D, completes on an mbarrier) -------------------------------
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

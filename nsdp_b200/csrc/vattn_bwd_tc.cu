@@ -518,8 +518,8 @@ __global__ void finalize_scatter_kernel(const float *__restrict__ tmp, float *__
 static long long segment_tiles() {
   static const long long v = [] {
     const char *e = getenv("NSDP_VATTN_SEG");
-    const long long t = e ? atoll(e) : 2048;
-    return t < 1 || t > 2048 ? 2048ll : t;
+    const long long t = e ? atoll(e) : 2072;   // 14 x 148 SMs: whole waves
+    return t < 1 || t > 2072 ? 2072ll : t;
   }();
   return v;
 }
@@ -711,13 +711,13 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
       uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
       auto wait_operand = [&]() {
-        mbar_wait(a_ready, ready_phase, err);
+        mbar_wait_poll(a_ready, ready_phase, err);
         ready_phase ^= 1;
         tc_fence_after();
       };
       // waits for the next slot of the ring; returns the B descriptor of its hi slab (lo slab = + SLAB / 16)
       auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
-        mbar_wait(&full[slot], slot_phase, err);
+        mbar_wait_poll(&full[slot], slot_phase, err);
         tc_fence_after();
         bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
         release = &empty[slot];

@@ -512,12 +512,12 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
       uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
       auto wait_operand = [&]() {
-        mbar_wait(a_ready, ready_phase, err);
+        mbar_wait_poll(a_ready, ready_phase, err);
         ready_phase ^= 1;
         tc_fence_after();
       };
       auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
-        mbar_wait(&full[slot], slot_phase, err);
+        mbar_wait_poll(&full[slot], slot_phase, err);
         tc_fence_after();
         bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
         release = &empty[slot];
