@@ -43,8 +43,8 @@ WORKLOAD = "configs[1]: forward-deformation TDNet, batch 8 shapes x 4096 surface
 VATTN_DEC_FWD_FLOP_PER_QUERY = 7 * (2 * 3 * 200 + 2 * 200 * 200) + 7 * (2 * 2 * 200 * 200)
 VATTN_DEC_BWD_FLOP_PER_QUERY = 2 * VATTN_DEC_FWD_FLOP_PER_QUERY
 # dram__bytes_read.sum + dram__bytes_write.sum of one decoder-attention backward op (13 chain + 13 reduction launches), from the
-# ncu --set full captures summarised in profiles/ncu_r1_summary.md (None until measured)
-NCU_TRAFFIC_BYTES_PER_OP = None
+# ncu --set full captures summarised in profiles/ncu_r1_summary.md
+NCU_TRAFFIC_BYTES_PER_OP = 34.8e9
 
 
 def measured_peaks():
