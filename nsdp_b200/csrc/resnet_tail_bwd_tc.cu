@@ -23,7 +23,7 @@ using namespace umma;
 constexpr int H = 128;
 constexpr int KS_H = H / 16;
 constexpr int SLAB_H = H * 16 * 2;        // [128 x 16] bf16 slab
-constexpr int STAGES = 3;
+constexpr int SLOT_BYTES = 2 * SLAB_H;   // 8 KB: one 128-row matrix k-step (hi + lo slab) or ONE slab of a wider matrix
 constexpr int NPART = 4;
 constexpr int WORKER_WARPS = 4 * NPART;
 constexpr int THREADS = (2 + WORKER_WARPS) * 32;
@@ -37,7 +37,13 @@ struct Cfg {
   static constexpr int CP = CP_;
   static constexpr int KS_C = CP / 16;
   static constexpr int SLAB_C = CP * 16 * 2;                       // [CP x 16] slab (d_lat products: N = CP)
-  static constexpr int STAGE_BYTES = 2 * (SLAB_C > SLAB_H ? SLAB_C : SLAB_H);
+  // The weight ring is addressed in 8 KB slots. A k-step of an H-row matrix (hi + lo slab) takes one slot; a k-step of a
+  // CP-row matrix (d_lat products) takes one slot if both slabs fit, else two (hi slab, lo slab). With 3 stages of
+  // 13 KB the ring could not cover the L2 latency: the MMAs ran at 170 cycles instead of 64 (trace, round 1).
+  static constexpr bool C_SPLIT = 2 * SLAB_C > SLOT_BYTES;
+  static constexpr int C_SLOTS = C_SPLIT ? 2 : 1;                  // slots per k-step of a CP-row matrix
+  static constexpr int STAGES = CP_ > 128 ? 6 : 8;                 // ring depth in slots
+  static constexpr int STAGE_BYTES = SLOT_BYTES;
   static constexpr int A_LAT_HALF = 128 * CP * 2;
   static constexpr int A_X_HALF = 128 * H * 2;
   static constexpr int LCHUNKS = CP / 8;
@@ -45,7 +51,7 @@ struct Cfg {
   static constexpr int OFF_LAT = 0;
   static constexpr int OFF_X = OFF_LAT + 2 * A_LAT_HALF;
   static constexpr int OFF_STAGE = OFF_X + 2 * A_X_HALF;
-  static constexpr int OFF_BSUM = OFF_STAGE + STAGES * STAGE_BYTES;   // float[MAXB + 1][H]
+  static constexpr int OFF_BSUM = OFF_STAGE + STAGES * SLOT_BYTES;    // float[MAXB + 1][H]
   static constexpr int OFF_B0 = OFF_BSUM + (MAXB + 1) * H * 4;         // float[MAXB][H]
   static constexpr int OFF_WO = OFF_B0 + MAXB * H * 4;                 // float4[H]
   static constexpr int OFF_DO = OFF_WO + H * 16;                       // float4[128]  dout rows of the tile
@@ -158,7 +164,7 @@ template <class C>
 __global__ void __launch_bounds__(THREADS, 1)
 resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout, float *__restrict__ d_lat,
                           const unsigned char *__restrict__ packed, const Staging stg, long long tile_begin,
-                          long long tile_end, int *err) {
+                          long long tile_end, int *err, unsigned long long *trace) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *L_hi = smem + C::OFF_LAT, *L_lo = L_hi + C::A_LAT_HALF;
   unsigned char *X_hi = smem + C::OFF_X, *X_lo = X_hi + C::A_X_HALF;
@@ -168,6 +174,7 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
   float4 *wos = reinterpret_cast<float4 *>(smem + C::OFF_WO);
   float4 *dos = reinterpret_cast<float4 *>(smem + C::OFF_DO);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+  constexpr int STAGES = C::STAGES;
   uint64_t *full = bars, *empty = bars + STAGES, *a_ready = bars + 2 * STAGES, *acc_done = a_ready + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
 
@@ -215,9 +222,11 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
     if (lane < PL) {
       const size_t fwd_bytes = fwd_region_bytes<C>(nb);
       const int nfwd = (1 + nb) * C::KS_C + 2 * nb * KS_H;
-      constexpr int PER_BLK = 3 * KS_H;                                   // w1b_i, w0b_i (2 KS_H x ST_H), wcb_{i+1} (KS_H x ST_C)
+      constexpr int CS = C::C_SLOTS;
+      constexpr int PER_BLK = 2 * KS_H + CS * KS_H;                       // w1b_i, w0b_i (2 KS_H slots), wcb_{i+1} (CS x KS_H slots)
       constexpr size_t BLK_BYTES = (size_t)2 * KS_H * ST_H + (size_t)KS_H * ST_C;
-      const int per_tile = nfwd + nb * PER_BLK + KS_H;                    // ... + wcb_0
+      constexpr uint32_t C_BYTES = ST_C / CS;                              // one slot of a CP-row k-step
+      const int per_tile = nfwd + nb * PER_BLK + CS * KS_H;               // ... + wcb_0
       const long long first = tile_begin + blockIdx.x;
       const long long my_tiles = first < tile_end ? (tile_end - first + gridDim.x - 1) / gridDim.x : 0;
       const long long total = my_tiles * per_tile;
@@ -230,10 +239,11 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
         } else {
           const int u = st - nfwd, blk = u / PER_BLK, w = u - blk * PER_BLK;
           if (blk < nb) {
-            src = packed + fwd_bytes + (size_t)blk * BLK_BYTES + (w < 2 * KS_H ? (size_t)w * ST_H : (size_t)2 * KS_H * ST_H + (size_t)(w - 2 * KS_H) * ST_C);
-            bytes = w < 2 * KS_H ? ST_H : ST_C;
+            src = packed + fwd_bytes + (size_t)blk * BLK_BYTES +
+                  (w < 2 * KS_H ? (size_t)w * ST_H : (size_t)2 * KS_H * ST_H + (size_t)(w - 2 * KS_H) * C_BYTES);
+            bytes = w < 2 * KS_H ? ST_H : C_BYTES;
           } else {
-            src = packed + fwd_bytes + (size_t)nb * BLK_BYTES + (size_t)(u - nb * PER_BLK) * ST_C; bytes = ST_C;
+            src = packed + fwd_bytes + (size_t)nb * BLK_BYTES + (size_t)(u - nb * PER_BLK) * C_BYTES; bytes = C_BYTES;
           }
         }
         const int s = (int)(it % STAGES);
@@ -255,31 +265,45 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
       const uint64_t xhi = smem_desc(smem_u32(X_hi), lbo_a, 128), xlo = smem_desc(smem_u32(X_lo), lbo_a, 128);
       const uint32_t stage_addr = smem_u32(stage0);
       uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
-      // A (hi/lo descriptors, `ksteps` k-steps) x the next `ksteps` weight stages of N = nrows -> TMEM column `col`
+      // A (hi/lo descriptors, `ksteps` k-steps) x the next weight k-steps of N = nrows -> TMEM column `col`
       auto gemm = [&](uint64_t a_hi, uint64_t a_lo, int ksteps, int nrows, uint32_t idesc, uint32_t col, bool fresh) {
         const uint32_t lbo_b = nrows * 16, slab = nrows * 32;
         const uint64_t bh0 = smem_desc(stage_addr, lbo_b, 128);
+        const bool split = C::C_SPLIT && nrows > H;   // hi slab and lo slab arrive in two slots
         for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ah = a_hi + ks * A_STEP, al = a_lo + ks * A_STEP;
           mbar_wait(&full[slot], slot_phase, err);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ah = a_hi + ks * A_STEP, al = a_lo + ks * A_STEP;
-            const uint64_t bh = bh0 + (uint64_t)slot * (C::STAGE_BYTES >> 4);
+            const uint64_t bh = bh0 + (uint64_t)slot * (SLOT_BYTES >> 4);
             mma_bf16(tmem_base + col, ah, bh, idesc, !(fresh && ks == 0));
             mma_bf16(tmem_base + col, al, bh, idesc, true);
-            mma_bf16(tmem_base + col, ah, bh + (slab >> 4), idesc, true);
+            if (!split) mma_bf16(tmem_base + col, ah, bh + (slab >> 4), idesc, true);
             mma_commit(&empty[slot]);
           }
           if (++slot == STAGES) { slot = 0; slot_phase ^= 1; }
+          if (split) {
+            mbar_wait(&full[slot], slot_phase, err);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t bl = bh0 + (uint64_t)slot * (SLOT_BYTES >> 4);
+              mma_bf16(tmem_base + col, ah, bl, idesc, true);
+              mma_commit(&empty[slot]);
+            }
+            if (++slot == STAGES) { slot = 0; slot_phase ^= 1; }
+          }
         }
       };
       auto commit_acc = [&]() {
+        TR(102);
         if (elect_one()) mma_commit(acc_done);
       };
       auto wait_ready = [&]() {
+        TR(100);
         mbar_wait(a_ready, ready_phase, err);
         ready_phase ^= 1;
         tc_fence_after();
+        TR(101);
       };
       for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         // ---- forward recompute ----
@@ -323,16 +347,25 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
     const int lch0 = part * C::LCHUNKS / NPART, lch1 = (part + 1) * C::LCHUNKS / NPART;
     uint32_t done_phase = 0;
 
+#ifdef NSDP_TRACE
+    const bool tr_on = (tid == 64);
+#define TW(id) do { if (tr_on) TR(id); } while (0)
+#else
+#define TW(id) do { } while (0)
+#endif
     auto wait_acc = [&]() {
+      TW(200);
       mbar_wait(acc_done, done_phase, err);
       done_phase ^= 1;
       tc_fence_after();
+      TW(201);
     };
     auto publish = [&]() {
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      TW(202);
     };
     // v[0..32) of this thread's hidden columns -> X operand (+ optional staged copy)
     auto put_x = [&](const float (&v)[XPT], unsigned char *stage_tile) {
@@ -540,7 +573,11 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     const long long t1 = t0 + seg < tiles ? t0 + seg : tiles;
     const long long n = t1 - t0;
     const int grid = (int)(n < num_sms() ? n : num_sms());
-    kern<<<grid, THREADS, C::SMEM, st>>>(a, dout, g.d_lat, packed, stg, t0, t1, err);
+    unsigned long long *trace = nullptr;
+#ifdef NSDP_TRACE
+    if (const char *tp = getenv("NSDP_TRACE_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
+#endif
+    kern<<<grid, THREADS, C::SMEM, st>>>(a, dout, g.d_lat, packed, stg, t0, t1, err, trace);
     rc = check_launch();
     if (rc != NSDP_OK) return rc;
     dwtc::Job jobs[24];

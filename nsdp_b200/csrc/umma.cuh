@@ -254,3 +254,19 @@ __host__ __device__ constexpr uint32_t canon_off(int rows, int row, int k) {
 
 }  // namespace umma
 }  // namespace nsdp
+
+#ifdef NSDP_TRACE
+// timeline of CTA 0 (debug builds only): (event id, clock64) pairs appended to a buffer whose address comes from the
+// environment (NSDP_TRACE_PTR, a device pointer to >= 64 KB of zeroed memory; word 0 = number of events)
+#define TR(id)                                                                              \
+  do {                                                                                      \
+    if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                              \
+      const unsigned long long n_ = atomicAdd(trace, 1ull);                                 \
+      if (n_ < 4000) { trace[1 + 2 * n_] = (unsigned long long)(id); trace[2 + 2 * n_] = (unsigned long long)clock64(); } \
+    }                                                                                       \
+  } while (0)
+#else
+#define TR(id) do { } while (0)
+#endif
+
+

@@ -598,20 +598,6 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
 //   * the per-centre inputs of the softmax backward (max, 1/sum, d_out, out) are loaded one half-chunk ahead.
 //   * staging precision: `lo` = 0 stages only the bf16 hi half of every operand tile (reductions over millions of rows).
 // =====================================================================================================================
-#ifdef NSDP_TRACE
-// timeline of CTA 0 (debug builds only): (event id, clock64) pairs appended to a buffer whose address comes from the
-// environment (NSDP_TRACE_PTR, a device pointer to >= 64 KB of zeroed memory; word 0 = number of events)
-#define TR(id)                                                                              \
-  do {                                                                                      \
-    if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                              \
-      const unsigned long long n_ = atomicAdd(trace, 1ull);                                 \
-      if (n_ < 4000) { trace[1 + 2 * n_] = (unsigned long long)(id); trace[2 + 2 * n_] = (unsigned long long)clock64(); } \
-    }                                                                                       \
-  } while (0)
-#else
-#define TR(id) do { } while (0)
-#endif
-
 struct OhStaging {
   unsigned char *h, *g, *da, *dgp, *ds, *e;
   int lo;   // 1: [hi slab][lo slab] per k-step, 0: hi slab only
