@@ -138,11 +138,19 @@ typedef struct {
   float sign;
   int impl;           /* 0 = auto (tensor-core kernel when the shape is instantiated, else CUDA cores),
                          1 = force the fp32 CUDA-core kernel, 2 = require the tcgen05 kernel */
+  void *saved;        /* optional opaque forward -> backward buffer of nsdp_vattn_saved_bytes() bytes (device memory), or
+                         NULL. When the forward call gets one (together with `stats`), it keeps the operand tiles and
+                         pre-softmax values of the pair level there and the backward call that receives the SAME buffer
+                         skips the recomputation of the forward chain. */
+  size_t saved_bytes; /* size of `saved` */
 } nsdp_vattn_args;
 
 /* `stats` (2,B,M,D) or NULL: when given, the per-(centre, channel) softmax max and 1/sum are stored for the
  * backward kernel. */
 size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args); /* packed bf16 hi/lo weight image (tcgen05 path) */
+/* bytes of the optional forward -> backward buffer `args->saved` (0: this shape / implementation keeps nothing and the
+ * backward recomputes the chain, which is what the reference-sized memory footprint asks for) */
+size_t nsdp_vattn_saved_bytes(const nsdp_vattn_args *args);
 int nsdp_vattn_fwd_f32(const nsdp_vattn_args *args, float *out /* (B,M,D) */, float *stats, void *workspace,
                        size_t workspace_bytes, void *stream);
 

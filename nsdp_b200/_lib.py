@@ -25,6 +25,7 @@ class VattnArgs(C.Structure):
         ("wd2", C.c_void_p), ("wp", C.c_void_p), ("wg2", C.c_void_p),
         ("B", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("D", C.c_int),
         ("has_global", C.c_int), ("sign", C.c_float), ("impl", C.c_int),
+        ("saved", C.c_void_p), ("saved_bytes", C.c_size_t),
     ]
 
 
@@ -68,6 +69,7 @@ SIGNATURES = {
     "nsdp_knn_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "nsdp_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "nsdp_vattn_fwd_workspace_bytes": (_SZ, [C.POINTER(VattnArgs)]),
+    "nsdp_vattn_saved_bytes": (_SZ, [C.POINTER(VattnArgs)]),
     "nsdp_vattn_fwd_f32": (_I, [C.POINTER(VattnArgs), _P, _P, _P, _SZ, _P]),
     "nsdp_vattn_bwd_workspace_bytes": (_SZ, [C.POINTER(VattnArgs)]),
     "nsdp_vattn_bwd_f32": (_I, [C.POINTER(VattnArgs), _P, _P, _P, C.POINTER(VattnGrads), _P, _SZ, _P]),

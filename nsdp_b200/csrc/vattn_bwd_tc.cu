@@ -1059,6 +1059,371 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+
+// =====================================================================================================================
+// "Saved" variant of the OH chain kernel: the forward call kept H, G (staged operand tiles) and the fp32 blocks a / acc1
+// of every tile in nsdp_vattn_args::saved, so the backward starts at the softmax backward: no H / E operands, no GEMM1,
+// no GEMM2, no G epilogue. Per tile: (a, acc1, mask <- saved) -> dS, dA -> GEMM3 -> dGP -> GEMM4a/b -> dpre. The
+// weight-gradient jobs read H and G straight from the saved buffer.
+// =====================================================================================================================
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+vattn_bwd_sv_kernel(const nsdp_vattn_args a, const float *__restrict__ out, const float *__restrict__ stats,
+                    const float *__restrict__ dout, const nsdp_vattn_grads g, const unsigned char *__restrict__ packed,
+                    const unsigned char *__restrict__ saved, long long tiles_total, const OhStaging stg, int tpb,
+                    long long tile_begin, long long tile_end, int *err) {
+  static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
+  using L = BwdLayout<C>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + L::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  float *scratch = reinterpret_cast<float *>(smem + L::OFF_A);  // aliases A once GEMM4b has consumed it
+  unsigned char *stage0 = smem + L::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + L::OFF_WD0);
+  float *vcs = reinterpret_cast<float *>(smem + L::OFF_VC);
+  float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
+  float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const int krows = a.K + 1;
+  const long long BM = (long long)a.B * a.M;
+  constexpr size_t TB = saved_tile_bytes<C>();
+  const unsigned char *sv_g = saved + (size_t)tiles_total * TB;        // staged G tiles (hi slab = ReLU mask source)
+  const unsigned char *sv_a = saved + (size_t)2 * tiles_total * TB;    // fp32 a blocks
+  const unsigned char *sv_s = saved + (size_t)3 * tiles_total * TB;    // fp32 acc1 blocks
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    vcs[kk] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < C::SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_ready, C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int PER_TILE = 3 * C::KSTEPS;            // GEMM3, GEMM4a, GEMM4b
+  constexpr int FIRST_SLOT = 3 * C::KSTEPS;          // their weights follow GEMM1 (2 slots / k-step) and GEMM2 in the image
+
+  if (warp == 0) {
+    // ===================== producer: backward-role weights; L2 prefetch of the next tile's saved blocks =====================
+    constexpr int PL = C::SLOTS / 2;
+    const long long first = tile_begin + blockIdx.x;
+    const long long my_tiles = first < tile_end ? (tile_end - first + gridDim.x - 1) / gridDim.x : 0;
+    if (lane < PL) {
+      const long long total = my_tiles * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const int j = (int)(it % PER_TILE);
+        const int s = (int)(it % C::SLOTS);
+        const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], C::SLOT_BYTES);
+        bulk_g2s(stage0 + (size_t)s * C::SLOT_BYTES, packed + (size_t)(FIRST_SLOT + j) * C::SLOT_BYTES, C::SLOT_BYTES, &full[s]);
+        if (j == 0) {   // one tile ahead: pull the saved a / acc1 / G blocks into L2 while this tile computes
+          const long long nt = first + (it / PER_TILE + 1) * gridDim.x;
+          if (nt < tile_end) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sv_a + (size_t)nt * TB), "r"((uint32_t)TB) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sv_s + (size_t)nt * TB), "r"((uint32_t)TB) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sv_g + (size_t)nt * TB), "r"((uint32_t)TB) : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (see vattn_bwd_oh_kernel) =====================
+    {
+      const uint32_t idesc = idesc_bf16(128, C::DP);
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = C::DP * 16;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+      for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int gi = 2; gi < 5; ++gi) {   // GEMM3 (-> acc0), GEMM4a (-> acc1), GEMM4b (acc1 +=)
+          mbar_wait(a_ready, ready_phase, err);
+          ready_phase ^= 1;
+          tc_fence_after();
+          const uint32_t d = tmem_base + (gi >= 3 ? C::ACC1_COL : 0);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            mbar_wait(&full[slot], slot_phase, err);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+              const uint64_t bh = bh0 + (uint64_t)slot * (C::SLOT_BYTES >> 4);
+              mma_bf16(d, ah, bh, idesc, gi == 4 || ks > 0);
+              mma_bf16(d, al, bh, idesc, true);
+              mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
+              mma_commit(&empty[slot]);
+            }
+            if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
+          }
+          if (elect_one()) mma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int ww = warp - 2;
+    const int wtid = tid - 64;
+    const int quarter = warp & 3;
+    const int part = ww >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t done_phase = 0;
+    constexpr int NQ = (C::CHUNKS + C::NPART - 1) / C::NPART;
+    constexpr int NE = (C::E_COLS / 8 + C::NPART - 1) / C::NPART;
+    static_assert(NQ * 8 <= 64, "ReLU mask of G is kept in one 64-bit register");
+    const int slabs = stg.lo ? 2 : 1;
+    const uint32_t a_base = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+    const size_t st_row = (size_t)(r >> 4) * (size_t)(slabs * C::DP * 32) + (size_t)(r & 15) * 16;
+    const size_t st_tile = (size_t)slabs * 256 * C::DP;
+    const size_t ste_row = (size_t)(r >> 4) * (size_t)(C::E_COLS * 32) + (size_t)(r & 15) * 16;
+    const size_t svg_row = (size_t)(r >> 4) * (size_t)(2 * C::DP * 32) + (size_t)(r & 15) * 16;   // saved G: always hi + lo
+    const size_t svf_row = (size_t)r * 32;
+    float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cb = 0.f;
+
+    auto wait_acc = [&]() {
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+    };
+    auto publish = [&]() {
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    };
+    auto emit = [&](const float (&x)[8], int ch, bool to_a, unsigned char *stage_tile, uint4 &hi, uint4 &lo) {
+      split2(x[0], x[1], hi.x, lo.x);
+      split2(x[2], x[3], hi.y, lo.y);
+      split2(x[4], x[5], hi.z, lo.z);
+      split2(x[6], x[7], hi.w, lo.w);
+      if (to_a) {
+        *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = hi;
+        *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = lo;
+      }
+      if (stage_tile) {
+        unsigned char *p = stage_tile + st_row + (size_t)ch * 256;
+        *reinterpret_cast<uint4 *>(p) = hi;
+        if (stg.lo) *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+      }
+    };
+
+    RowInfoPB ri = row_info_pb<C>(a, tile_begin + blockIdx.x, r, krows, tpb);
+    for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      const size_t tl = (size_t)(tile - tile_begin);
+      const bool row_on = ri.c >= 0;
+      const int b = (int)(tile / tpb);
+      if (part == 0) rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
+      unsigned long long gmaskbits = 0ull;
+      // ---- one-hot tile for the table-gradient jobs (staged only: no GEMM reads it here) ----------------------------------
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::E_COLS / 8) {
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if ((ri.j >> 3) == ch) {
+            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;
+            const int w = (ri.j & 7) >> 1;
+            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(stg.e + tl * (size_t)(256 * C::E_COLS) + ste_row + (size_t)ch * 256) = e;
+        }
+      }
+      // ---- w = exp(a - max) / sum, s = acc1 + vc; ds = w * dout, da = ds * (s - out) ---------------------------------------
+      //      a, acc1 and the ReLU mask come from the forward's saved blocks (L2-prefetched one tile ahead), the per-centre
+      //      softmax inputs as in vattn_bwd_oh_kernel; everything is loaded one half-chunk ahead
+      {
+        const float *st_mx = stats + (size_t)(row_on ? ri.c : 0) * D;
+        const float *st_iv = stats + ((size_t)BM + (row_on ? ri.c : 0)) * D;
+        const float *p_go = dout + (size_t)(row_on ? ri.c : 0) * D;
+        const float *p_o = out + (size_t)(row_on ? ri.c : 0) * D;
+        const unsigned char *pa = sv_a + (size_t)tile * TB + svf_row;
+        const unsigned char *ps = sv_s + (size_t)tile * TB + svf_row;
+        const unsigned char *pg = sv_g + (size_t)tile * TB + svg_row;
+        struct Half { float4 mx, iv, go, o, av, sv; };
+        auto load_half = [&](int hc, Half &h) {
+          const int ch = part + (hc >> 1) * C::NPART;
+          const int col = ch * 8 + (hc & 1) * 4;
+          h.mx = h.iv = h.go = h.o = h.av = h.sv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_on && col < D) {
+            h.mx = ldg4(st_mx + col); h.iv = ldg4(st_iv + col); h.go = ldg4(p_go + col); h.o = ldg4(p_o + col);
+            h.av = __ldg(reinterpret_cast<const float4 *>(pa + (size_t)ch * 4096 + (hc & 1) * 16));
+            h.sv = __ldg(reinterpret_cast<const float4 *>(ps + (size_t)ch * 4096 + (hc & 1) * 16));
+          }
+        };
+        Half cur, nxt2;
+        load_half(0, cur);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          float ds[8], da[8];
+          uint4 gh = make_uint4(0u, 0u, 0u, 0u);
+          if (ch < C::CHUNKS && row_on) gh = __ldg(reinterpret_cast<const uint4 *>(pg + (size_t)ch * 256));
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            load_half(q * 2 + half + 1, nxt2);
+            if (ch < C::CHUNKS) {
+              const float4 v0 = *reinterpret_cast<const float4 *>(vcs + ch * 8 + half * 4);
+              const float avs[4] = {cur.av.x, cur.av.y, cur.av.z, cur.av.w}, svs[4] = {cur.sv.x, cur.sv.y, cur.sv.z, cur.sv.w};
+              const float mxs[4] = {cur.mx.x, cur.mx.y, cur.mx.z, cur.mx.w}, ivs[4] = {cur.iv.x, cur.iv.y, cur.iv.z, cur.iv.w};
+              const float gos[4] = {cur.go.x, cur.go.y, cur.go.z, cur.go.w}, os[4] = {cur.o.x, cur.o.y, cur.o.z, cur.o.w};
+              const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
+              const bool on = row_on && ch * 8 + half * 4 < D;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = half * 4 + u;
+                const float w = on ? __expf(avs[u] - mxs[u]) * ivs[u] : 0.f;
+                ds[j] = w * gos[u];
+                da[j] = ds[j] * (svs[u] + vv[u] - os[u]);
+              }
+            }
+            cur = nxt2;
+          }
+          if (ch < C::CHUNKS) {
+            const uint32_t gw[4] = {gh.x, gh.y, gh.z, gh.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if ((gw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu) gmaskbits |= 1ull << (q * 8 + j);
+            uint4 hi, lo;
+            emit(da, ch, true, stg.da + tl * st_tile, hi, lo);
+            emit(ds, ch, false, stg.ds + tl * st_tile, hi, lo);
+            const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
+            tmem_st8(trow + C::ACC1_COL + ch * 8, pk);
+          }
+        }
+      }
+      tmem_st_wait();
+      publish();
+      // ---- while GEMM3 runs: the next tile's row description -------------------------------------------------------------
+      const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
+      // ---- GEMM3 done: A is free -> operand ds from its parked words (GEMM4a) ---------------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          uint32_t pk[8];
+          tmem_ld8u(trow + C::ACC1_COL + ch * 8, pk);
+          *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      publish();
+      // ---- dgp = dg * [g > 0] (reads acc0 while GEMM4a fills acc1): staged + parked in acc0's columns ---------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          float dg[8];
+          tmem_ld8(trow + ch * 8, dg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dg[j] = ((gmaskbits >> (q * 8 + j)) & 1ull) ? dg[j] : 0.f;
+          uint4 hi, lo;
+          emit(dg, ch, false, stg.dgp + tl * st_tile, hi, lo);
+          const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
+          tmem_st8(trow + ch * 8, pk);
+        }
+      }
+      tmem_st_wait();
+      // ---- GEMM4a done: A is free -> operand dgp (GEMM4b) ----------------------------------------------------------------------
+      wait_acc();
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          uint32_t pk[8];
+          tmem_ld8u(trow + ch * 8, pk);
+          *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      publish();
+      // ---- dpre = dh * [h > 0]; d rel; dpre -> fp32 scratch (aliases A, free once GEMM4b is done) ------------------------------
+      wait_acc();
+      {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            float dh[8];
+            tmem_ld8(trow + C::ACC1_COL + ch * 8, dh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = ch * 8 + j;
+              const float4 w0 = wd0s[col];
+              const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+              const float dp = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
+              sx = fmaf(dp, w0.x, sx); sy = fmaf(dp, w0.y, sy); sz = fmaf(dp, w0.z, sz);
+              if (col < D) scratch[(size_t)col * L::SCR_LD + ((r + col) & 127)] = dp;
+            }
+          }
+        }
+        relacc[(part * 3 + 0) * 128 + r] = sx;
+        relacc[(part * 3 + 1) * 128 + r] = sy;
+        relacc[(part * 3 + 2) * 128 + r] = sz;
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
+      if (wtid < D) {
+        const float *colp = scratch + (size_t)wtid * L::SCR_LD;
+#pragma unroll 4
+        for (int rr = 0; rr < 128; ++rr) {
+          const float dp = colp[(rr + wtid) & 127];
+          const float4 rl = rels[rr];
+          cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
+        }
+      }
+      if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < C::NPART; ++pp) {
+          sx += relacc[(pp * 3 + 0) * 128 + r];
+          sy += relacc[(pp * 3 + 1) * 128 + r];
+          sz += relacc[(pp * 3 + 2) * 128 + r];
+        }
+        if (g.d_xyz_c) {
+          float *dst = g.d_xyz_c + (size_t)ri.c * 3;
+          atomicAdd(dst, a.sign * sx); atomicAdd(dst + 1, a.sign * sy); atomicAdd(dst + 2, a.sign * sz);
+        }
+        if (g.d_xyz_n) {
+          float *dst = g.d_xyz_n + ((size_t)b * a.N + ri.j) * 3;
+          atomicAdd(dst, -a.sign * sx); atomicAdd(dst + 1, -a.sign * sy); atomicAdd(dst + 2, -a.sign * sz);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
+      ri = nxt;
+    }
+    if (wtid < D) {
+      if (g.d_wd0) {
+        atomicAdd(g.d_wd0 + wtid * 3 + 0, cw0); atomicAdd(g.d_wd0 + wtid * 3 + 1, cw1); atomicAdd(g.d_wd0 + wtid * 3 + 2, cw2);
+      }
+      if (g.d_bd0) atomicAdd(g.d_bd0 + wtid, cb);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
 // dT1 / dT2 [B][E_COLS][D] (rows <= N valid) -> d_kp, d_gq, d_pc / d_vp, d_gv, d_vc (see the table definitions in
 // vattn_fwd_oh_kernel): one thread per (shape, column)
 template <class C>
@@ -1087,6 +1452,11 @@ __global__ void finalize_tables_kernel(const float *__restrict__ dt1, const floa
 static bool stage_lo_for(long long /*pair_rows*/) {
   static const int forced = [] { const char *e = getenv("NSDP_STAGE_LO"); return e ? atoi(e) : 1; }();
   return forced != 0;
+}
+
+static bool no_saved() {
+  static const bool v = [] { const char *e = getenv("NSDP_NO_SAVED"); return e && atoi(e) != 0; }();
+  return v;
 }
 
 template <class C>
@@ -1126,18 +1496,28 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
   pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables);
   rc = check_launch();
   if (rc != NSDP_OK) return rc;
+  const bool use_saved = a.saved && a.saved_bytes >= saved_bytes_total<C>(tiles) && !no_saved();
+  const unsigned char *saved = (const unsigned char *)a.saved;
   auto kern = vattn_bwd_oh_kernel<C>;
+  auto kern_sv = vattn_bwd_sv_kernel<C>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<C>::SMEM);
   if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaFuncSetAttribute(kern_sv, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<C>::SMEM);
+  if (e != cudaSuccess) return cuda_rc(e);
+  constexpr size_t TB = saved_tile_bytes<C>();
   for (long long t0 = 0; t0 < tiles; t0 += seg) {
     const long long t1 = t0 + seg < tiles ? t0 + seg : tiles;
     const long long n = t1 - t0;
     const int grid = (int)(n < num_sms() ? n : num_sms());
-    unsigned long long *trace = nullptr;
+    if (use_saved) {
+      kern_sv<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, g, packed, saved, tiles, stg, tpb, t0, t1, err);
+    } else {
+      unsigned long long *trace = nullptr;
 #ifdef NSDP_TRACE
-    if (const char *tp = getenv("NSDP_TRACE_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
+      if (const char *tp = getenv("NSDP_TRACE_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
 #endif
-    kern<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, g, packed, tables, stg, tpb, t0, t1, err, trace);
+      kern<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, g, packed, tables, stg, tpb, t0, t1, err, trace);
+    }
     rc = check_launch();
     if (rc != NSDP_OK) return rc;
     // weight gradients over the whole segment + table gradients per shape (tile ranges relative to the segment)
@@ -1148,14 +1528,18 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
       nj = 0;
       return r2;
     };
-    auto wjob = [&](const unsigned char *x, const unsigned char *y, float *o) {
+    auto wjob = [&](const unsigned char *x, int xlo, const unsigned char *y, float *o) {
       dwtc::Job j{x, y, o, C::DP, C::DP, a.D, a.D, a.D, nullptr, nullptr, 0, 0, 0};
-      j.x_lo = lo; j.y_lo = lo;
+      j.x_lo = xlo; j.y_lo = lo;
       return j;
     };
-    jobs[nj++] = wjob(stg.g, stg.da, g.d_wg2t);
-    jobs[nj++] = wjob(stg.h, stg.dgp, g.d_wpt);
-    jobs[nj++] = wjob(stg.h, stg.ds, g.d_wd2t);
+    // H and G: from this segment's staging, or (saved variant) straight from the forward's buffer, always hi + lo there
+    const unsigned char *xh = use_saved ? saved + (size_t)t0 * TB : stg.h;
+    const unsigned char *xg = use_saved ? saved + (size_t)(tiles + t0) * TB : stg.g;
+    const int xlo = use_saved ? 1 : lo;
+    jobs[nj++] = wjob(xg, xlo, stg.da, g.d_wg2t);
+    jobs[nj++] = wjob(xh, xlo, stg.dgp, g.d_wpt);
+    jobs[nj++] = wjob(xh, xlo, stg.ds, g.d_wd2t);
     for (long long b = t0 / tpb; b * tpb < t1; ++b) {
       const long long r0 = (b * tpb > t0 ? b * tpb : t0) - t0, r1 = ((b + 1) * tpb < t1 ? (b + 1) * tpb : t1) - t0;
       for (int m = 0; m < 2; ++m) {

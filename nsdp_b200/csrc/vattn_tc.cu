@@ -428,7 +428,7 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
 vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed,
                     const unsigned char *__restrict__ tables, float *__restrict__ out, float *__restrict__ stats,
-                    int tpb, long long tiles, int *err) {
+                    unsigned char *__restrict__ saved, int tpb, long long tiles, int *err) {
   static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *A_hi = smem + C::OFF_A;
@@ -581,6 +581,10 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
     constexpr int NQ = (C::CHUNKS + C::NPART - 1) / C::NPART;           // chunk rounds per thread
     constexpr int NE = (C::E_COLS / 8 + C::NPART - 1) / C::NPART;       // one-hot chunk rounds per thread
     const int g8 = lane & 7;
+    // forward -> backward buffer (training): staged H / G tiles and the fp32 a / acc1 blocks of every tile
+    constexpr size_t TB = saved_tile_bytes<C>();
+    const size_t sv_st = (size_t)(r >> 4) * (size_t)(2 * C::DP * 32) + (size_t)(r & 15) * 16;   // + chunk * 256 (staged layout)
+    const size_t sv_f32 = (size_t)r * 32;                                                       // + chunk * 4096 (fp32 blocks)
 
     RowInfoPB ri = row_info_pb<C>(a, blockIdx.x, r, krows, tpb);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -606,6 +610,11 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           const uint32_t off = canon_off(128, r, k0);
           *reinterpret_cast<uint4 *>(A_hi + off) = hi;
           *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+          if (saved) {
+            unsigned char *p = saved + (size_t)tile * TB + sv_st + (size_t)ch * 256;
+            *reinterpret_cast<uint4 *>(p) = hi;
+            *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+          }
         }
       }
 #pragma unroll
@@ -650,6 +659,11 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           const uint32_t off = canon_off(128, r, k0);
           *reinterpret_cast<uint4 *>(A_hi + off) = hi;
           *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+          if (saved) {
+            unsigned char *p = saved + (size_t)(tiles + tile) * TB + sv_st + (size_t)ch * 256;
+            *reinterpret_cast<uint4 *>(p) = hi;
+            *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+          }
         }
       }
       tc_fence_before();
@@ -673,6 +687,12 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           float av[8], sv[8];
           tmem_ld8(trow + k0, av);
           tmem_ld8(trow + C::ACC1_COL + k0, sv);
+          if (saved) {
+            float4 *pa = reinterpret_cast<float4 *>(saved + (size_t)(2 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
+            float4 *ps = reinterpret_cast<float4 *>(saved + (size_t)(3 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
+            pa[0] = make_float4(av[0], av[1], av[2], av[3]); pa[1] = make_float4(av[4], av[5], av[6], av[7]);
+            ps[0] = make_float4(sv[0], sv[1], sv[2], sv[3]); ps[1] = make_float4(sv[4], sv[5], sv[6], sv[7]);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) av[j] = row_on ? av[j] : -INFINITY;
           // transpose inside the 8-lane group: afterwards this lane holds column k0 + g8 of all 8 rows of the centre
@@ -730,7 +750,8 @@ static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *w
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return cuda_rc(e);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, tpb, tiles, err);
+  unsigned char *saved = (stats && a.saved && a.saved_bytes >= saved_bytes_total<C>(tiles)) ? (unsigned char *)a.saved : nullptr;
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, saved, tpb, tiles, err);
   return check_launch();
 }
 
@@ -803,6 +824,14 @@ extern "C" size_t nsdp_vattn_fwd_workspace_bytes(const nsdp_vattn_args *args) {
     case 4: return vtc::packed_bytes<vtc::TcCfg<256, 128>>() + 16;
     default: return 0;
   }
+}
+
+extern "C" size_t nsdp_vattn_saved_bytes(const nsdp_vattn_args *args) {
+  using namespace nsdp;
+  if (!args || args->impl == 1 || vtc::pick(*args) != 1 || !vtc::oh_ok(*args) || vtc::no_onehot()) return 0;
+  using Cfg = vtc::TcCfg<208, 8, 4, true>;
+  const long long tiles = (long long)args->B * ((args->M + Cfg::CENTRES - 1) / Cfg::CENTRES);
+  return vtc::saved_bytes_total<Cfg>(tiles);
 }
 
 namespace nsdp {

@@ -209,6 +209,20 @@ __device__ __forceinline__ float group_transpose_max(float (&v)[8], int lane) {
   return v[0];
 }
 
+// ---- forward -> backward buffer of the OH kernels (nsdp_vattn_args::saved) ---------------------------------------------------------
+// Four blocks of `tiles` x SAVED_TILE bytes: [H staged][G staged][a][acc1]. H and G are the operand tiles in the staged
+// k-step-major bf16 hi/lo layout of dw_tc.cu (they feed the weight-gradient jobs directly, and G > 0 is the ReLU mask);
+// a (GEMM2 result, pre-softmax) and acc1 (GEMM1's second accumulator, s = acc1 + vc) are fp32 in [chunk][row][8] order,
+// i.e. byte(r, ch) = (ch * 128 + r) * 32: a warp reads / writes 1 KB contiguous.
+template <class C>
+constexpr size_t saved_tile_bytes() {
+  return (size_t)512 * C::DP;
+}
+template <class C>
+constexpr size_t saved_bytes_total(long long tiles) {
+  return (size_t)tiles * 4 * saved_tile_bytes<C>();
+}
+
 // ---- per-shape anchor tables of the OH kernels (see vattn_fwd_oh_kernel), packed like the weights ------------------------
 template <class C>
 constexpr size_t table_bytes_per_shape() {

@@ -235,7 +235,8 @@ def test_vattn_tc_decoder_forward(M, shape_query, monkeypatch):
         assert (got_tc - want).abs().max().item() < 3e-5 * scale
 
 
-def test_vattn_oh_backward_multi_segment(monkeypatch):
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-activations"])
+def test_vattn_oh_backward_multi_segment(save, monkeypatch):
     """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 1250 tiles vs
     segments of 2048): the one-hot chain kernel + weight / per-shape table gradient jobs against the fp32 CUDA-core
     backward on the same inputs."""
@@ -243,6 +244,7 @@ def test_vattn_oh_backward_multi_segment(monkeypatch):
     names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
     go = torch.randn(3, 20000, 200, generator=torch.Generator().manual_seed(5)).to(DEV)
     grads = {}
+    monkeypatch.setattr(ops, "SAVE_ACTIVATIONS", save)   # forward -> backward buffer (nsdp_vattn_args::saved) on / off
     for impl in (1, 2):
         monkeypatch.setattr(ops, "VATTN_IMPL", impl)
         dev = {k: (v.to(DEV).contiguous().requires_grad_(True) if k in names else (v.to(DEV) if torch.is_tensor(v) else v))
