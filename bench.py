@@ -47,6 +47,12 @@ VATTN_DEC_BWD_FLOP_PER_QUERY = 2 * VATTN_DEC_FWD_FLOP_PER_QUERY
 NCU_TRAFFIC_BYTES_PER_OP = 34.8e9
 
 
+def emit_line(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout (everything else this process prints goes to stderr)."""
+    sys.__stdout__.write(json.dumps(line) + "\n")
+    sys.__stdout__.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -157,7 +163,7 @@ def run_reference_arm(args):
             "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (oracle port), bounded sample"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -277,7 +283,7 @@ def run_ours(args):
         # products (2 M-tiles x 3 terms) + 2 table-gradient products (2 terms) over 8 k-steps of 16 rows
         mma = 2 * 128 * 208 * 16
         tiles = B_PER_GPU * ((N_QUERY + 15) // 16)
-        executed = tiles * mma * ((6 * 13 * 3 + 28) + 8 * (3 * 2 * 3 + 2 * 2))
+        executed = tiles * mma * ((6 * 13 * 3 + 28) + 8 * (3 * 2 * 3 + 2 * 2))   # recompute path (SAVE_ACTIVATIONS off)
         executed_tflops = executed / (bwd_ms * 1e-3) / 1e12
         roof = {"kernel": "nsdp_vattn_bwd_f32 for the decoder cross-attention (D=200, 7+1 rows/query): tcgen05 one-hot chain "
                           "kernel vattn_bwd_oh_kernel (13 segment launches) + split-K gradient reduction dw_tc_kernel (weight and "
@@ -314,7 +320,7 @@ def run_ours(args):
                 "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         td.destroy_process_group()
 
@@ -327,10 +333,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    import contextlib
+    # the API mirrors the reference's progress prints (optimizer specs, parameter counts): keep stdout for the JSON line
+    with contextlib.redirect_stdout(sys.stderr):
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
