@@ -26,13 +26,17 @@ def optimizer_factory(config, parameters):
         "interval": config.get("lr_step", 100),
         "factor": config.get("lr_decay", 0.1),
     })
+    parameters = list(parameters)
     group = {"params": parameters, "lr": schedule.get_learning_rate(0),
              "weight_decay": config.get("weight_decay", 0.0)}
     if name == "SGD":
         group["momentum"] = config.get("momentum", 0.9)
         return schedule, torch.optim.SGD([group])
     if name == "Adam":
-        return schedule, torch.optim.Adam([group])
+        # same update rule and state_dict layout as the reference's torch.optim.Adam; on the GPU the whole step is one
+        # fused kernel instead of ~30 multi-tensor launches
+        fused = len(parameters) > 0 and all(p.is_cuda for p in parameters)
+        return schedule, torch.optim.Adam([group], fused=fused)
     raise NotImplementedError()
 
 
