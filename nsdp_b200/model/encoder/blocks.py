@@ -39,6 +39,14 @@ def _pointwise(conv: nn.Conv1d, x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, conv.weight.squeeze(-1), conv.bias)
 
 
+def _fused_linear(x: torch.Tensor, weights):
+    """[F.linear(x, w) for w in weights] as ONE GEMM against the row-concatenated weights (the per-point projections of a
+    block share their input; three or four [B*n, d] x [d, d] launches become one, forward and backward), returned as
+    contiguous tensors (the kernels take dense (B, n, d) tables)."""
+    outs = F.linear(x, torch.cat(list(weights), dim=0)).split([w.shape[0] for w in weights], dim=-1)
+    return [o.contiguous() for o in outs]
+
+
 def fold_pair_mlps(fc_delta: nn.Sequential, fc_gamma: nn.Sequential):
     """Kernel-side weights for one (fc_delta, fc_gamma) pair: see nsdp_vattn_args."""
     wd0, bd0 = fc_delta[0].weight, fc_delta[0].bias
@@ -79,9 +87,7 @@ class TransformerBlock(nn.Module):
             res = ops.vector_attention(xyz, xyz, idx, None, None, None, sign=1.0, **w)
         else:
             wg0 = self.fc_gamma[0].weight
-            qp = F.linear(feats, wg0 @ self.w_qs.weight)
-            kp = F.linear(feats, wg0 @ self.w_ks.weight)
-            vp = self.w_vs(feats)
+            qp, kp, vp = _fused_linear(feats, (wg0 @ self.w_qs.weight, wg0 @ self.w_ks.weight, self.w_vs.weight))
             res = ops.vector_attention(xyz, xyz, idx, qp, kp, vp, sign=1.0, **w) + feats
         return _bn_rows(self.bn, res)
 
@@ -137,19 +143,18 @@ class TransformerSetAbstraction(nn.Module):
 
         w1 = fold_pair_mlps(self.fc_delta1, self.fc_gamma1)
         g10 = self.fc_gamma1[0].weight
+        g20 = self.fc_gamma2[0].weight
         qp = F.linear(centre, g10 @ self.w_qs.weight)
-        kp = F.linear(points, g10 @ self.w_ks.weight)
-        vp = self.w_vs(points)
+        # the four projections of the full cloud (both attention stages) share their input: one GEMM
+        kp, vp, kp2, vp2 = _fused_linear(points, (g10 @ self.w_ks.weight, self.w_vs.weight, g20 @ self.w_ks2.weight,
+                                                  self.w_vs2.weight))
         # rel = neighbour - centre (blocks.py:295) -> sign = -1
         res1 = ops.vector_attention(new_xyz, xyz, idx, qp, kp, vp, sign=-1.0, **w1)
         res1 = res1 + _pointwise(self.conv2, F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, res1))))
         res1 = _bn_rows(self.bnorm0, res1)
 
         w2 = fold_pair_mlps(self.fc_delta1, self.fc_gamma2)  # same delta MLP, second gamma MLP
-        g20 = self.fc_gamma2[0].weight
         qp2 = F.linear(res1, g20 @ self.w_qs2.weight)
-        kp2 = F.linear(points, g20 @ self.w_ks2.weight)
-        vp2 = self.w_vs2(points)
         res2 = ops.vector_attention(new_xyz, xyz, idx, qp2, kp2, vp2, sign=-1.0, **w2)
 
         out = _bn_rows(self.bnorm1, res1 + res2) + centre
