@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from nsdp_b200 import ops
-from nsdp_b200.model.encoder.blocks import fold_pair_mlps
+from nsdp_b200.model.encoder.blocks import _fused_linear, fold_pair_mlps
 from nsdp_b200.model.utils import knn_indices
 
 
@@ -43,12 +43,11 @@ class CrossTransformerBlock(nn.Module):
         idx = knn_indices(xyz_q, xyz, min(self.nneigh, xyz.shape[1]))
         w = fold_pair_mlps(self.fc_delta, self.fc_gamma)
         wg0, bg0 = self.fc_gamma[0].weight, self.fc_gamma[0].bias
-        q = self.w_qs(lat_rep)                                   # (B, d): one query vector per SHAPE
-        k_anchor = self.w_ks(points)                             # (B, A, d)
+        # projections that share an input run as one GEMM each (latent code: q, global key, global value; anchors: k, v)
+        q, k_glob, gv = _fused_linear(lat_rep, (self.w_qs.weight, self.w_k_global.weight, self.w_v_global.weight))
+        k_anchor, vp = _fused_linear(points, (self.w_ks.weight, self.w_vs.weight))   # (B, A, d) each
         kp = F.linear(k_anchor - q[:, None, :], wg0)             # Wg0 (K_j - q): the kernel subtracts it
-        vp = self.w_vs(points)
-        gq = F.linear(q - self.w_k_global(lat_rep), wg0, bg0)    # global row: delta = 0 (blocks.py:79-80)
-        gv = self.w_v_global(lat_rep)
+        gq = F.linear(q - k_glob, wg0, bg0)                      # global row: delta = 0 (blocks.py:79-80)
         res = ops.vector_attention(xyz_q, xyz, idx, None, kp.contiguous(), vp.contiguous(), sign=1.0,
                                    gq=gq.contiguous(), gv=gv.contiguous(), **w)
         if not self.reduce_dim:

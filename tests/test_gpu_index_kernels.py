@@ -87,6 +87,18 @@ def test_knn_matches_oracle(M, N, k):
     assert torch.equal(d2.cpu(), wd2)  # distances bit-identical (same association, no FMA)
 
 
+@pytest.mark.parametrize("k", [16, 32, 64])
+def test_knn_full_c5_size(k):
+    """BASELINE.json configs[4]: 4096 queries (the FPS picks) against a 100 000-point cloud, k = 16 / 32 / 64; indices and
+    distances bit-exact against the C oracle (B = 1 keeps the scalar oracle at a few seconds)."""
+    xyz = synth.surface_cloud(1, 100000, seed=11, fp16_grid=False)
+    q = xyz[:, torch.randperm(100000, generator=torch.Generator().manual_seed(k))[:4096]].contiguous()
+    got, d2 = ops.knn(q.to(DEV), xyz.to(DEV), k, return_d2=True)
+    want, wd2 = orc.knn(q, xyz, k, return_d2=True)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(d2.cpu(), wd2)
+
+
 def test_knn_ties_are_lowest_index_first():
     pts = (torch.randint(-3, 4, (2, 600, 3)).float() * 0.25)
     got, d2 = ops.knn(pts.to(DEV), pts.to(DEV), 16, return_d2=True)
