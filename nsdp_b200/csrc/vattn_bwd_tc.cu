@@ -506,7 +506,8 @@ __global__ void finalize_scatter_kernel(const float *__restrict__ tmp, float *__
   if (c >= D) return;
   const long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
   float s = 0.f;
-  for (long long r = r0; r < r1; ++r) {
+#pragma unroll 8
+  for (long long r = r0; r < r1; ++r) {   // ~32 rows per block, loads batched by the unroll (the pass is pure streaming)
     const float v = tmp[r * D + c];
     s += v;
     if (dst) dst[r * D + c] += v;
@@ -580,7 +581,7 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
     if (rc != NSDP_OK) return rc;
   }
   const long long rows = (long long)a.B * a.N;
-  dim3 fgrid((unsigned)ceil_div(a.D, 128), (unsigned)(rows < 1024 ? ceil_div(rows, 8ll) : 128));
+  dim3 fgrid((unsigned)ceil_div(a.D, 128), (unsigned)(rows < 1024 ? ceil_div(rows, 8ll) : (rows / 32 < 2048 ? rows / 32 : 2048)));
   finalize_scatter_kernel<<<fgrid, 128, 0, st>>>(tmp_vp, a.vp ? g.d_vp : nullptr, g.d_vc, 1.f, rows, a.D);
   finalize_scatter_kernel<<<fgrid, 128, 0, st>>>(tmp_kp, a.kp ? g.d_kp : nullptr, g.d_pc, -1.f, rows, a.D);
   return check_launch();
