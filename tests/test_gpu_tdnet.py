@@ -71,6 +71,24 @@ def test_forward_against_oracle_multi_shape_fp16_grid(schemas):
     assert _mean_l2(got.cpu().numpy(), want.numpy()) < TOL
 
 
+def test_forward_full_size_shape_against_oracle(schemas):
+    """One shape at BASELINE.json's full size (4096 surface points on the fp16 grid, 50 000 spatial queries): anchors
+    bit-exact (two FPS levels on 4096 points with real ties), flow within the 1e-4 tolerance of the CPU oracle. The batch
+    of 8 such shapes of the bench differs only by the batch dimension (BatchNorm is in eval mode here)."""
+    model = _model(schemas, "forward").eval()
+    batch = synth.forward_batch(1, 4096, 50000, seed=1234, fp16_grid=True)
+    cfg = synth.make_config("forward")["model"]
+    sd = synth.named_state_dict([(k, s) for k, s in schemas["forward"]], seed=0)
+    trace = {}
+    with torch.no_grad():
+        want = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg, False, trace=trace)
+        surf = batch["surface_samples_inputs"].to(DEV)
+        enc = model.encode(surf)
+        got = model.decode(batch["space_samples_src"].to(DEV), enc)
+    assert torch.equal(enc["anchors"].cpu(), trace["anchors"])
+    assert _mean_l2(got.cpu().numpy(), want.numpy()) < TOL
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["fp32-cuda-cores", "auto-tcgen05"])
 def test_training_step_against_reference_golden(golden, schemas, impl, monkeypatch):
     """fwd + bwd through the CUDA kernels (train-mode BatchNorm): loss, prediction, d/d query coordinates,
