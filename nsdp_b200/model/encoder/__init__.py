@@ -1,7 +1,8 @@
+from nsdp_b200.model.encoder.pointnetplusplus import PointNetPlusPlusEncoder
 from nsdp_b200.model.encoder.pointransformer import PointTransformerEncoder
 
-# The reference also registers 'pointnet++' (model/encoder/__init__.py:4-7), an ablation no shipped config
-# selects; it is out of the hot-path scope and deliberately absent here.
+# same registry as the reference (model/encoder/__init__.py:4-7); 'pointnet++' is its ablation encoder
 encoder_dict = {
+    "pointnet++": PointNetPlusPlusEncoder,
     "pointransformer": PointTransformerEncoder,
 }

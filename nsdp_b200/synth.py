@@ -44,6 +44,18 @@ def make_config(model_type: str = "forward") -> dict:
                                        "weight_decay": 0.0}}
 
 
+def make_ablation_config() -> dict:
+    """The reference's ablation blocks behind the same registries: PointNet++-style encoder (max-pool set abstraction)
+    and the interpolation decoder (model/encoder/__init__.py:4-7, model/decoder/__init__.py:5-8)."""
+    cfg = make_config("forward")
+    cfg["model"]["encoder"] = "pointnet++"
+    cfg["model"]["encoder_kwargs"] = {"npoints_per_layer": [5000, 500, 100], "nneighbor": 16, "d_transformer": 256,
+                                      "nfinal_transformers": 3}
+    cfg["model"]["decoder"] = "interp"
+    cfg["model"]["decoder_kwargs"] = {"dim_inp": 256, "dim": 200, "hidden_dim": 128, "out_dim": 3}
+    return cfg
+
+
 def _bumpy_sphere(rng: np.random.Generator, n: int, phase: float) -> Tuple[np.ndarray, np.ndarray]:
     """n points on a smooth closed surface of radius ~0.35 and their (approximate) normals."""
     v = rng.standard_normal((n, 3))
