@@ -105,3 +105,29 @@ def shard_batch(data_dict: dict, rank: Optional[int] = None, world: Optional[int
         else:
             out[k] = v
     return out
+
+
+@torch.no_grad()
+def sharded_decode(decode_fn, points: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    """Inference-time query sharding: the decoder is independent per query point, so with the
+    (cheap, replicated) encoding computed on every rank, rank r decodes the contiguous query slice
+    [r*Q/W, (r+1)*Q/W) of `points` (B, Q, 3) and the slices are all-gathered back into (B, Q, C) on every rank — meshes
+    with millions of vertices (test.py:127-151, run.py:121-139) decode W times faster. `decode_fn(points_slice)` is
+    e.g. `lambda p: model.decode(p, encoding)`. Without a process group this is just `decode_fn(points)`."""
+    if rank is None:
+        rank = td.get_rank() if is_active() else 0
+    if world is None:
+        world = td.get_world_size() if is_active() else 1
+    if world == 1:
+        return decode_fn(points)
+    Q = points.shape[1]
+    per = (Q + world - 1) // world                        # equal-sized slices: the last one is padded with its first query
+    lo, hi = min(rank * per, Q), min((rank + 1) * per, Q)
+    mine = points[:, lo:hi]
+    if mine.shape[1] < per:
+        pad = (mine[:, :1] if mine.shape[1] else points[:, :1]).expand(-1, per - mine.shape[1], -1)
+        mine = torch.cat([mine, pad], dim=1)
+    out = decode_fn(mine.contiguous()).contiguous()
+    parts = [torch.empty_like(out) for _ in range(world)]
+    td.all_gather(parts, out)
+    return torch.cat(parts, dim=1)[:, :Q]

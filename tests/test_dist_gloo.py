@@ -58,6 +58,38 @@ def test_dp_allreduce_world2():
     assert torch.count_nonzero(unused0) == 0 and torch.count_nonzero(unused1) == 0
 
 
+def _decode_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    pts = torch.arange(2 * 7 * 3, dtype=torch.float32).reshape(2, 7, 3)    # Q = 7 is not divisible by 2: padded slice
+    seen = []
+
+    def decode(p):                                                          # stand-in for model.decode(p, encoding)
+        seen.append(p.shape[1])
+        return p * 2.0 + 1.0
+
+    out = nd.sharded_decode(decode, pts)
+    q.put((rank, out, seen))
+    td.destroy_process_group()
+
+
+def test_query_sharded_decode_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_decode_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.arange(2 * 7 * 3, dtype=torch.float32).reshape(2, 7, 3) * 2.0 + 1.0
+    for rank, out, seen in res:
+        assert torch.equal(out, want)          # every rank ends with all queries, in order
+        assert seen == [4]                     # ... having decoded only its (padded) slice
+
+
 def test_inactive_without_process_group():
     model = torch.nn.Linear(2, 2)
     model(torch.ones(1, 2)).sum().backward()
@@ -67,3 +99,5 @@ def test_inactive_without_process_group():
     assert nd.shard_batch({"x": torch.zeros(4, 1)})["x"].shape[0] == 4
     with pytest.raises(ValueError):
         nd.shard_batch({"x": torch.zeros(5, 1)}, rank=0, world=2)
+    pts = torch.rand(1, 5, 3)
+    assert torch.equal(nd.sharded_decode(lambda p: p + 1.0, pts), pts + 1.0)   # no process group: plain decode
