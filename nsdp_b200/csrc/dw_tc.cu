@@ -24,11 +24,15 @@ using namespace umma;
 constexpr int MAX_STAGES = 8;   // ring depth is chosen per launch: as many stages as fit in shared memory (HBM latency)
 constexpr int THREADS = 6 * 32;  // warp 0 producer, warp 1 MMA, warps 2..5 flush
 constexpr int MAX_JOBS = 24;
+constexpr int MAX_CHUNKS = 64;
 
 struct Params {
   Job jobs[MAX_JOBS];
   int njobs;
   int cta_begin[MAX_JOBS + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split the tile range of job j
+  int nchunks;                   // > 0: chunk-aligned mode, CTA = (chunk blockIdx / njobs, job blockIdx % njobs)
+  int chunk_t0[MAX_CHUNKS + 1];
+  int chunk_shape[MAX_CHUNKS];
   int stages;              // ring depth (<= MAX_STAGES)
   uint32_t ones_off;       // offset of the constant one-hot operand (column sums by MMA) inside dynamic shared memory
   int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
@@ -42,11 +46,23 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int jid = 0;
-  while (jid + 1 < p.njobs && (int)blockIdx.x >= p.cta_begin[jid + 1]) ++jid;
-  const int splits = p.cta_begin[jid + 1] - p.cta_begin[jid], split = (int)blockIdx.x - p.cta_begin[jid];
-  const Job job = p.jobs[jid];
-  const long long jt = job.t1 - job.t0;
-  const long long t0 = job.t0 + jt * split / splits, t1 = job.t0 + jt * (split + 1) / splits;
+  long long t0, t1;
+  Job job;
+  if (p.nchunks > 0) {
+    const int c = (int)blockIdx.x / p.njobs;
+    jid = (int)blockIdx.x - c * p.njobs;
+    job = p.jobs[jid];
+    t0 = p.chunk_t0[c];
+    t1 = p.chunk_t0[c + 1];
+    job.out += (long long)p.chunk_shape[c] * job.out_shape_stride;
+  } else {
+    while (jid + 1 < p.njobs && (int)blockIdx.x >= p.cta_begin[jid + 1]) ++jid;
+    const int splits = p.cta_begin[jid + 1] - p.cta_begin[jid], split = (int)blockIdx.x - p.cta_begin[jid];
+    job = p.jobs[jid];
+    const long long jt = job.t1 - job.t0;
+    t0 = job.t0 + jt * split / splits;
+    t1 = job.t0 + jt * (split + 1) / splits;
+  }
   const uint32_t xs = (uint32_t)job.wx * 32, ys = (uint32_t)job.wy * 32;  // slab bytes
   const uint32_t xk = job.x_lo ? 2 * xs : xs, yk = job.y_lo ? 2 * ys : ys;   // k-step pitch inside a staged tile
   const bool x_lo = job.x_lo && p.terms >= 2, y_lo = job.y_lo && p.terms >= 3;   // which lo slabs are streamed at all
@@ -281,6 +297,7 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
     total += cost[i];
   }
   p.njobs = njobs;
+  p.nchunks = 0;
   // CTAs per job: proportional to bytes, at least 1, at most the job's tile count; about one CTA per SM in total
   const int budget = num_sms() > njobs ? num_sms() : njobs;
   int ctas = 0;
@@ -307,6 +324,58 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
   dw_tc_kernel<<<ctas, THREADS, smem, st>>>(p);
+  return check_launch();
+}
+
+int dw_tc_launch_chunked(const dwtc::Job *jobs, int njobs, long long tiles, const long long *bounds, int nshapes, int *err,
+                         cudaStream_t st) {
+  using namespace dwtc;
+  if (njobs <= 0 || njobs > MAX_JOBS || tiles <= 0 || nshapes <= 0) return NSDP_ERR_INVALID_ARGUMENT;
+  static const bool off = [] { const char *e = getenv("NSDP_DW_NO_CHUNKS"); return e && atoi(e) != 0; }();
+  if (off || nshapes > MAX_CHUNKS / 2 || tiles > 0x7fffffffll) return NSDP_ERR_UNSUPPORTED;
+  Params p;
+  p.terms = dw_terms();
+  size_t max_stage = 0;
+  for (int i = 0; i < njobs; ++i) {
+    Job j = jobs[i];
+    if (j.wx % 16 || j.wy % 16 || j.wx > 256 || j.wy > 256 || j.gsum) return NSDP_ERR_UNSUPPORTED;
+    j.t0 = 0; j.t1 = tiles;
+    p.jobs[i] = j;
+    const size_t stage = (size_t)32 * (j.wx * ((j.x_lo && p.terms >= 2) ? 2 : 1) + j.wy * ((j.y_lo && p.terms >= 3) ? 2 : 1));
+    max_stage = stage > max_stage ? stage : max_stage;
+  }
+  p.njobs = njobs;
+  // about one CTA per SM in total: P chunks, dealt out to the shapes by length (at least one each), uniform inside a shape
+  int P = num_sms() / njobs;
+  if (P < nshapes) P = nshapes;
+  if (P > MAX_CHUNKS) P = MAX_CHUNKS;
+  int nc = 0;
+  p.chunk_t0[0] = 0;
+  for (int s = 0; s < nshapes; ++s) {
+    const long long len = bounds[s + 1] - bounds[s];
+    if (len <= 0) return NSDP_ERR_INVALID_ARGUMENT;
+    long long n = (len * P + tiles / 2) / tiles;
+    if (n < 1) n = 1;
+    if (n > len) n = len;
+    if (nc + n > MAX_CHUNKS) n = MAX_CHUNKS - nc;
+    if (n < 1) return NSDP_ERR_UNSUPPORTED;
+    for (long long c = 0; c < n; ++c) {
+      p.chunk_shape[nc] = s;
+      p.chunk_t0[nc + 1] = (int)(bounds[s] + len * (c + 1) / n);
+      ++nc;
+    }
+  }
+  p.nchunks = nc;
+  p.err = err;
+  int stages = (int)((227 * 1024 - 2 * 4096 - 1024) / max_stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return NSDP_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.ones_off = (uint32_t)((size_t)stages * max_stage + 4096);
+  const size_t smem = (size_t)stages * max_stage + 2 * 4096;
+  cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  dw_tc_kernel<<<nc * njobs, THREADS, smem, st>>>(p);
   return check_launch();
 }
 

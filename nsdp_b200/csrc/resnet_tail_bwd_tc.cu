@@ -595,7 +595,11 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     // init_enc: d pre_0 = d net_0 = dn_0 as well
     jobs[nj++] = {stg.lat, stg.dn[0], g.d_wc_t, C::CP, H, a.C, H, wld, g.d_bc, nullptr, 0, 0, 0};
     for (int j = 0; j < nj; ++j) jobs[j].x_lo = jobs[j].y_lo = lo;
-    rc = dw_tc_launch(jobs, nj, n, err, st);
+    // chunk-aligned launch: every job walks the same tile chunks at the same time, so `lat` (six readers), dn_i (two) and
+    // x_i / y_i come from HBM once and from L2 for the other readers
+    const long long bounds[2] = {0, n};
+    rc = dw_tc_launch_chunked(jobs, nj, n, bounds, 1, err, st);
+    if (rc == NSDP_ERR_UNSUPPORTED) rc = dw_tc_launch(jobs, nj, n, err, st);
     if (rc != NSDP_OK) return rc;
   }
   return NSDP_OK;

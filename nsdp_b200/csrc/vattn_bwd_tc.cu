@@ -1541,6 +1541,26 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
     jobs[nj++] = wjob(xg, xlo, stg.da, g.d_wg2t);
     jobs[nj++] = wjob(xh, xlo, stg.dgp, g.d_wpt);
     jobs[nj++] = wjob(xh, xlo, stg.ds, g.d_wd2t);
+    // chunk-aligned launch first: weight and table jobs walk the same tile chunks, so dGP / dS / H are read from HBM once
+    {
+      const long long b0 = t0 / tpb;
+      long long bounds[40];
+      int ns = 0;
+      bounds[0] = 0;
+      for (long long b = b0; b * tpb < t1 && ns < 38; ++b) bounds[++ns] = ((b + 1) * tpb < t1 ? (b + 1) * tpb : t1) - t0;
+      if (bounds[ns] == n) {
+        dwtc::Job cj[5] = {jobs[0], jobs[1], jobs[2], {}, {}};
+        for (int m = 0; m < 2; ++m) {
+          dwtc::Job j{stg.e, m == 0 ? stg.dgp : stg.ds, (m == 0 ? dt1 : dt2) + (size_t)b0 * C::E_COLS * a.D, C::E_COLS, C::DP,
+                      a.N + 1, a.D, a.D, nullptr, nullptr, 0, 0, 0};
+          j.x_lo = 0; j.y_lo = lo; j.out_shape_stride = (long long)C::E_COLS * a.D;
+          cj[3 + m] = j;
+        }
+        rc = dw_tc_launch_chunked(cj, 5, n, bounds, ns, err, st);
+        if (rc == NSDP_OK) continue;
+        if (rc != NSDP_ERR_UNSUPPORTED) return rc;
+      }
+    }
     for (long long b = t0 / tpb; b * tpb < t1; ++b) {
       const long long r0 = (b * tpb > t0 ? b * tpb : t0) - t0, r1 = ((b + 1) * tpb < t1 ? (b + 1) * tpb : t1) - t0;
       for (int m = 0; m < 2; ++m) {
