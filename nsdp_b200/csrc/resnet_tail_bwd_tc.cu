@@ -520,7 +520,16 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-constexpr long long kSegmentTiles = 592;   // 4 x 148 SMs: whole waves. staging: (CP + 22*128 + 16) * 512 B per tile ~ 1.5 MB -> 0.8 GB per segment
+static long long tail_segment_tiles() {
+  static const long long v = [] {
+    const char *e = getenv("NSDP_TAIL_SEG");
+    const long long t = e ? atoll(e) : 1184;   // 8 x 148 SMs: whole waves; 1.85 GB of staging per segment
+    return t < 1 || t > 4736 ? 1184ll : t;
+  }();
+  return v;
+}
+#define kSegmentTiles tail_segment_tiles()
+//   // 4 x 148 SMs: whole waves. staging: (CP + 22*128 + 16) * 512 B per tile ~ 1.5 MB -> 0.8 GB per segment
 
 template <class C>
 static size_t staged_bytes_per_tile(int nb) {
