@@ -515,12 +515,12 @@ __global__ void finalize_scatter_kernel(const float *__restrict__ tmp, float *__
   if (colsum) atomicAdd(colsum + c, sign * s);
 }
 
-// staging workspace = 5 tensors x 2048 tiles x 104 KB = 1.06 GB (NSDP_VATTN_SEG overrides the segment length)
+// staging workspace = 5 tensors x 4144 tiles x 104 KB = 2.2 GB per segment (NSDP_VATTN_SEG overrides the segment length)
 static long long segment_tiles() {
   static const long long v = [] {
     const char *e = getenv("NSDP_VATTN_SEG");
-    const long long t = e ? atoll(e) : 2072;   // 14 x 148 SMs: whole waves
-    return t < 1 || t > 2072 ? 2072ll : t;
+    const long long t = e ? atoll(e) : 4144;   // 28 x 148 SMs: whole waves (sweep 296 ... 12 432: longer is slightly better)
+    return t < 1 || t > 16576 ? 4144ll : t;
   }();
   return v;
 }

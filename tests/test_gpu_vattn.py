@@ -237,12 +237,12 @@ def test_vattn_tc_decoder_forward(M, shape_query, monkeypatch):
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-activations"])
 def test_vattn_oh_backward_multi_segment(save, monkeypatch):
-    """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 1250 tiles vs
-    segments of 2048): the one-hot chain kernel + weight / per-shape table gradient jobs against the fp32 CUDA-core
+    """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 2250 tiles vs
+    segments of 4144): the one-hot chain kernel + weight / per-shape table gradient jobs against the fp32 CUDA-core
     backward on the same inputs."""
-    case = _rand_case(B=3, M=20000, N=100, K=7, D=200, has_global=True, seed=21, shape_query=True)
+    case = _rand_case(B=3, M=36000, N=100, K=7, D=200, has_global=True, seed=21, shape_query=True)
     names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
-    go = torch.randn(3, 20000, 200, generator=torch.Generator().manual_seed(5)).to(DEV)
+    go = torch.randn(3, 36000, 200, generator=torch.Generator().manual_seed(5)).to(DEV)
     grads = {}
     monkeypatch.setattr(ops, "SAVE_ACTIVATIONS", save)   # forward -> backward buffer (nsdp_vattn_args::saved) on / off
     for impl in (1, 2):
