@@ -220,6 +220,32 @@ int nsdp_resnet_tail_bwd_f32(const nsdp_tail_args *args, const float *d_out /* (
                              const nsdp_tail_grads *grads, void *workspace, size_t workspace_bytes,
                              void *stream);
 
+/* Plain fused neural-field MLP over query rows (BASELINE.json configs[3], SURVEY.md §8b "nsdp_fused_mlp_fwd": the
+ * decoder-only microbenchmark of the pattern model/decoder/crosstransformer_decoder.py:63-69 applies to every
+ * spatial sample — one small weight stack, every row independent):
+ *     h = relu(x W_in + b_in);  for l < n_hidden: h = relu(h W_l + b_l);  out = h W_out + b_out
+ * i.e. 2 + n_hidden nn.Linear layers with ReLU between them. x (R, Cin), Cin <= 4; out (R, O), O <= 4;
+ * width W <= 256 and a multiple of 4 (tcgen05 kernel: W in {16, 32, 64, 128, 256}, 1 <= n_hidden <= 7; everything else,
+ * and impl == 1, runs the fp32 CUDA-core kernel). Weights are passed transposed (K-major), like nsdp_tail_args:
+ *     w_in_t (Cin, W), b_in (W);  w_h_t (n_hidden, W, W) with w_h_t[l][k][n] = W_l[n][k], b_h (n_hidden, W);
+ *     w_out_t (W, O), b_out (O).
+ * The activations never leave the SM: HBM traffic is 4 (Cin + O) bytes per row; the packed weights stream from L2.
+ * reuse_packed != 0: `workspace` still holds the packed weight image written by an earlier call with the same
+ * weights and shapes (inference: weights are constant), so the packing kernel is skipped. */
+typedef struct {
+  const float *x;
+  const float *w_in_t, *b_in;
+  const float *w_h_t, *b_h;
+  const float *w_out_t, *b_out;
+  int R, Cin, W, O, n_hidden;
+  int impl;          /* 0 = auto, 1 = fp32 CUDA-core kernel, 2 = require tcgen05 */
+  int reuse_packed;
+} nsdp_mlp_args;
+
+size_t nsdp_fused_mlp_fwd_workspace_bytes(const nsdp_mlp_args *args);
+int nsdp_fused_mlp_fwd_f32(const nsdp_mlp_args *args, float *out /* (R,O) */, void *workspace, size_t workspace_bytes,
+                           void *stream);
+
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
  * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.

@@ -49,6 +49,15 @@ class TailGrads(C.Structure):
         "d_lat", "d_wc_t", "d_bc", "d_w0_t", "d_b0", "d_w1_t", "d_b1", "d_wo_t", "d_bo")]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w_in_t", C.c_void_p), ("b_in", C.c_void_p),
+        ("w_h_t", C.c_void_p), ("b_h", C.c_void_p), ("w_out_t", C.c_void_p), ("b_out", C.c_void_p),
+        ("R", C.c_int), ("Cin", C.c_int), ("W", C.c_int), ("O", C.c_int), ("n_hidden", C.c_int),
+        ("impl", C.c_int), ("reuse_packed", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/nsdp_b200.h declares
 # (tests/test_abi.py cross-checks this table against the header).
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -77,6 +86,8 @@ SIGNATURES = {
     "nsdp_resnet_tail_fwd_f32": (_I, [C.POINTER(TailArgs), _P, _P, _SZ, _P]),
     "nsdp_resnet_tail_bwd_workspace_bytes": (_SZ, [C.POINTER(TailArgs)]),
     "nsdp_resnet_tail_bwd_f32": (_I, [C.POINTER(TailArgs), _P, C.POINTER(TailGrads), _P, _SZ, _P]),
+    "nsdp_fused_mlp_fwd_workspace_bytes": (_SZ, [C.POINTER(MlpArgs)]),
+    "nsdp_fused_mlp_fwd_f32": (_I, [C.POINTER(MlpArgs), _P, _P, _SZ, _P]),
     "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 

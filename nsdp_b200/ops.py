@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import TailArgs, TailGrads, VattnArgs, VattnGrads, check
+from ._lib import MlpArgs, TailArgs, TailGrads, VattnArgs, VattnGrads, check
 
 LAUNCHES = 0  # number of libnsdp_b200 kernel-launching calls made (bench.py reports it)
 
@@ -388,3 +388,58 @@ class _ResnetTail(torch.autograd.Function):
 def resnet_tail(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
     """Fused decoder ResNet-FC tail over rows: (R,C) -> (R,O). See nsdp_tail_args."""
     return _ResnetTail.apply(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Plain fused neural-field MLP (BASELINE.json configs[3]; forward / inference only)
+# ---------------------------------------------------------------------------------------------------
+class FusedMLP:
+    """h = relu(x W_in + b_in); n_hidden x { h = relu(h W_l + b_l) }; out = h W_out + b_out over rows (R, Cin) -> (R, O).
+
+    Takes the weights in nn.Linear layout (out_features, in_features) — `w_in (W, Cin)`, `w_h (n_hidden, W, W)`,
+    `w_out (O, W)` — transposes them once, and keeps the packed tensor-core weight image between calls (weights are
+    constant at inference time), so a call is ONE kernel launch. See nsdp_mlp_args in include/nsdp_b200.h."""
+
+    def __init__(self, w_in, b_in, w_h, b_h, w_out, b_out, impl: int = 0):
+        for n, t in dict(w_in=w_in, b_in=b_in, w_h=w_h, b_h=b_h, w_out=w_out, b_out=b_out).items():
+            _chk_f32(n, t)
+        self.W, self.Cin = w_in.shape
+        self.O = w_out.shape[0]
+        self.n_hidden = w_h.shape[0]
+        self.impl = impl
+        self.w_in_t = w_in.t().contiguous()
+        self.w_h_t = w_h.transpose(1, 2).contiguous()
+        self.w_out_t = w_out.t().contiguous()
+        self.b_in, self.b_h, self.b_out = b_in, b_h, b_out
+        self._ws = None
+        self._packed = False
+
+    def _args(self, x: torch.Tensor) -> MlpArgs:
+        a = MlpArgs()
+        a.x, a.w_in_t, a.b_in = _p(x), _p(self.w_in_t), _p(self.b_in)
+        a.w_h_t, a.b_h, a.w_out_t, a.b_out = _p(self.w_h_t), _p(self.b_h), _p(self.w_out_t), _p(self.b_out)
+        a.R, a.Cin, a.W, a.O, a.n_hidden = x.shape[0], self.Cin, self.W, self.O, self.n_hidden
+        a.impl = self.impl
+        a.reuse_packed = 1 if self._packed else 0
+        return a
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _chk_f32("x", x)
+        if x.dim() != 2 or x.shape[1] != self.Cin:
+            raise RuntimeError(f"x must be (R, {self.Cin})")
+        a = self._args(x)
+        if out is None:
+            out = torch.empty((a.R, a.O), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            ws_bytes = L.nsdp_fused_mlp_fwd_workspace_bytes(C.byref(a))
+            if ws_bytes and (self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != x.device):
+                self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+                self._packed = False
+                a.reuse_packed = 0
+            with _timed("fused_mlp_fwd"):
+                check(L.nsdp_fused_mlp_fwd_f32(C.byref(a), out.data_ptr(), _p(self._ws) if ws_bytes else None, ws_bytes,
+                                               _stream()), "nsdp_fused_mlp_fwd_f32")
+            self._packed = bool(ws_bytes)
+        _count()
+        return out

@@ -1,0 +1,78 @@
+"""BASELINE.json configs[3] microbenchmark: decoder-only fused MLP, 1 000 000 query points x (3 -> W, 6 x (W -> W), W -> 3),
+width sweep W in {16, 32, 64, 128, 256} (W = 16 sits below the machine's ridge point and is judged against
+the HBM roofline, W >= 32 against the tensor peak).
+
+CUDA-event timing around each call on the launching stream, 5 warm-up + 30 timed calls, median. Every call reads a
+different (x, out) pair from a rotating set whose total size exceeds the 126 MB L2, so inputs come from HBM.
+Printed next to ours: the same MLP as torch eager ops (cuBLAS fp32 addmm + relu, TF32 off and on) — the way the
+reference's decoder runs such a stack on a GPU."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from nsdp_b200 import ops
+from oracle import mlp_oracle   # seeded weights only (tools/ is not product code)
+
+DEV = "cuda:0"
+R, L = int(os.environ.get("C4_ROWS", 1_000_000)), 6
+NBUF = 12   # 12 x (12 MB in + 12 MB out) = 288 MB > L2
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) \
+    else {"hbm_gbs": 6551.0, "bf16_tflops": 1637.7}
+
+
+def timed(fn, reps=30, warm=5):
+    for i in range(warm):
+        fn(i)
+    ts = []
+    for i in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(i); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[len(ts) // 10], ts[(9 * len(ts)) // 10]
+
+
+g = torch.Generator().manual_seed(5)
+xs = [(torch.rand(R, 3, generator=g) - 0.5).to(DEV) for _ in range(NBUF)]
+outs = [torch.empty(R, 3, device=DEV) for _ in range(NBUF)]
+rows = []
+for W in (16, 32, 64, 128, 256):
+    w = [torch.from_numpy(t).to(DEV) for t in mlp_oracle.synth_mlp(W, L, seed=W)]
+    net = ops.FusedMLP(*w, impl=0)
+    ms, p10, p90 = timed(lambda i: net(xs[i % NBUF], outs[i % NBUF]))
+    w_in, b_in, w_h, b_h, w_out, b_out = w
+
+    def eager(i):
+        h = torch.relu(torch.addmm(b_in, xs[i % NBUF], w_in.t()))
+        for l in range(L):
+            h = torch.relu(torch.addmm(b_h[l], h, w_h[l].t()))
+        return torch.addmm(b_out, h, w_out.t())
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ms_eager, _, _ = timed(eager, reps=10, warm=3)
+    err = float((eager(0) - net(xs[0])).abs().max())
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ms_tf32, _, _ = timed(eager, reps=10, warm=3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    flop = 2.0 * (3 * W + L * W * W + W * 3)
+    tfl = R * flop / (ms * 1e-3) / 1e12
+    gbs = R * 24 / (ms * 1e-3) / 1e9
+    intensity = flop / 24.0
+    ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    rows.append({
+        "W": W, "rows": R, "layers": L + 2, "ms": ms, "ms_p10": p10, "ms_p90": p90,
+        "points_per_s": R / (ms * 1e-3), "algorithmic_tflops": tfl, "executed_mma_tflops": 3 * R * 2.0 * L * W * W / (ms * 1e-3) / 1e12,
+        "hbm_gbs_compulsory": gbs, "flop_per_byte": intensity, "bound": "hbm" if intensity < ridge else "tensor",
+        "frac_hbm_peak": gbs / peaks["hbm_gbs"], "frac_tensor_peak": tfl / peaks["bf16_tflops"],
+        "frac_tensor_peak_executed": 3 * R * 2.0 * L * W * W / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+        "torch_eager_fp32_ms": ms_eager, "torch_eager_tf32_ms": ms_tf32, "speedup_vs_eager_fp32": ms_eager / ms,
+        "speedup_vs_eager_tf32": ms_tf32 / ms, "max_abs_diff_vs_eager_fp32": err,
+    })
+    print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
+print(json.dumps({"config": "configs[3]: 1M query points, 3 -> W, 6 x (W -> W), W -> 3, fp32 in/out, bf16x3 tcgen05",
+                  "peaks": {"hbm_gbs": peaks["hbm_gbs"], "bf16_tflops": peaks["bf16_tflops"]}, "sweep": rows}, indent=1))
