@@ -152,9 +152,60 @@ def cpu_reference_run(steps: int, warmup: int, shapes_per_step: int = 1, max_sec
                       f"torch CPU fp32 ({dt / max(done, 1):.2f} s/step)"}, dt / max(done, 1), done
 
 
+def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU):
+    """NOT the contract's reference arm (that one is the CPU run below): the same restatement of the reference's op chain
+    executed as PyTorch eager ops on cuda:0 (TF32 off; FPS = the reference's own CUDA kernel from oracle/_ref; k-NN = the
+    reference's square_distance + argsort) — the "reference on 1 GPU" number BASELINE.json's >= 10x target is stated
+    against. `--impl reference --ref-device cuda`."""
+    from nsdp_b200 import synth
+    from nsdp_b200.model import build_model
+    from oracle import tdnet_oracle as orc
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    cfg = synth.make_config("forward")
+    model, *_ = build_model(cfg)
+    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    sd = {k: v.to(dev) for k, v in synth.named_state_dict(schema, seed=0).items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if k.rsplit(".", 1)[-1] in ("weight", "bias")]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    batch = {k: v.to(dev) for k, v in synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234).items()}
+
+    def step():
+        opt.zero_grad()
+        pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
+                                 training=True)
+        loss = orc.l2_loss(pred, batch["space_samples_tgt"])
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return shapes_per_step * N_QUERY / (ms * 1e-3), ms, torch.cuda.max_memory_allocated() / 2 ** 30
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.ref_device == "cuda":
+        qps, ms, gib = gpu_reference_run(args.steps, args.warmup)
+        emit_line({"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                   "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                   "vs_baseline": None, "dtype": "f32 (TF32 off)", "data": "synthetic",
+                   "config": {"workload": WORKLOAD, "peak_memory_gib": gib,
+                              "note": "restatement of the reference op chain as PyTorch eager on cuda:0 with the reference's "
+                                      "own FPS kernel (oracle/_ref); informational, not the contract's CPU reference arm"}})
         return
     base, s_per_step, done = cpu_reference_run(args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -332,6 +383,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cuda = the reference op chain as PyTorch eager on one GPU (informational)")
     args = ap.parse_args()
     import contextlib
     # the API mirrors the reference's progress prints (optimizer specs, parameter counts): keep stdout for the JSON line

@@ -5,8 +5,11 @@ The reference has no distributed code at all (device hard-wired to cuda:0, train
 what sits behind the unchanged train_on_batch_* functions: they call allreduce_gradients(model) between
 backward() and optimizer.step(); it is a no-op unless a process group exists.
 
-BatchNorm semantics: local per-rank batch statistics (what DistributedDataParallel would give the
+BatchNorm semantics: by default local per-rank batch statistics (what DistributedDataParallel would give the
 reference). The all-reduce averages gradients so that the mean-loss semantics match a single-process batch.
+Optional `syncbn` mode (NSDP_B200_SYNCBN=1 or convert_sync_batchnorm(model)): every BatchNorm1d reduces
+(sum x, sum x^2, count) over all ranks, which reproduces the single-process batch-32 numbers of SURVEY.md §8e
+(outputs, gradients and running statistics) at the cost of two tiny collectives per layer and step.
 """
 from __future__ import annotations
 
@@ -39,6 +42,8 @@ def maybe_init_from_env(model, device) -> None:
         return
     init_process_group()
     broadcast_parameters(model)
+    if os.environ.get("NSDP_B200_SYNCBN", "0") == "1":
+        convert_sync_batchnorm(model)
 
 
 @torch.no_grad()
@@ -131,3 +136,62 @@ def sharded_decode(decode_fn, points: torch.Tensor, rank: Optional[int] = None, 
     parts = [torch.empty_like(out) for _ in range(world)]
     td.all_gather(parts, out)
     return torch.cat(parts, dim=1)[:, :Q]
+
+
+# ---------------------------------------------------------------------------------------------------
+# optional: BatchNorm statistics over the GLOBAL batch (SURVEY.md §8e "syncbn")
+# ---------------------------------------------------------------------------------------------------
+class _SyncBatchNormFn(torch.autograd.Function):
+    """y = (x - mean) * invstd * weight + bias with mean / var over the rows of ALL ranks. x is (R, C)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        C = x.shape[1]
+        packed = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+        packed[:C] = x.sum(0)
+        packed[C:2 * C] = (x * x).sum(0)
+        packed[2 * C] = x.shape[0]
+        td.all_reduce(packed, op=td.ReduceOp.SUM)
+        n = packed[2 * C]
+        mean = packed[:C] / n
+        var = (packed[C:2 * C] / n - mean * mean).clamp_min_(0.0)
+        invstd = torch.rsqrt(var + eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(momentum * mean)
+                running_var.mul_(1 - momentum).add_(momentum * var * (n / (n - 1)))   # unbiased, like nn.BatchNorm1d
+        xhat = (x - mean) * invstd
+        ctx.save_for_backward(xhat, weight, invstd, n)
+        return xhat * weight + bias
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, weight, invstd, n = ctx.saved_tensors
+        C = xhat.shape[1]
+        sums = torch.cat([dy.sum(0), (dy * xhat).sum(0)])
+        d_bias, d_weight = sums[:C].clone(), sums[C:].clone()          # parameter gradients stay LOCAL sums; the flat gradient
+        td.all_reduce(sums, op=td.ReduceOp.SUM)                        # all-reduce averages them like every other parameter
+        dx = (weight * invstd) * (dy - sums[:C] / n - xhat * (sums[C:] / n))
+        return dx, d_weight, d_bias, None, None, None, None
+
+
+class SyncBatchNorm1d(torch.nn.BatchNorm1d):
+    """nn.BatchNorm1d (same parameters, buffers and state_dict keys) whose training-mode statistics span all ranks.
+    Falls back to the parent's behaviour in eval mode and when no process group is active."""
+
+    def forward(self, x):
+        if not (self.training and is_active()) or x.dim() != 2:
+            return super().forward(x)
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return _SyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                      self.momentum, self.eps)
+
+
+def convert_sync_batchnorm(model):
+    """In-place: every nn.BatchNorm1d of `model` becomes a SyncBatchNorm1d (the mirror applies BN to (B*n, C) rows, see
+    model/encoder/blocks.py `_bn_rows`). state_dict keys and values are untouched."""
+    for m in model.modules():
+        if type(m) is torch.nn.BatchNorm1d:
+            m.__class__ = SyncBatchNorm1d
+    return model

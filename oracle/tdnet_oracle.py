@@ -42,7 +42,15 @@ def _lib():
 # index kernels (C restatement, oracle/nsdp_oracle.c)
 # --------------------------------------------------------------------------------------
 def fps(xyz: torch.Tensor, m: int) -> torch.Tensor:
-    """sampling_gpu.cu:69-173 + sampling.cpp:66-87 -> (B, m) int32."""
+    """sampling_gpu.cu:69-173 + sampling.cpp:66-87 -> (B, m) int32.
+    CUDA tensors (bench.py --impl reference --ref-device cuda only): the reference's own kernel, rebuilt by
+    oracle/build_ref.py."""
+    if xyz.is_cuda:
+        from oracle import ref_ext
+        ext = ref_ext.load()
+        if ext is None:
+            raise RuntimeError("oracle/_ref is not built: the GPU run of the reference path needs the reference's FPS kernel")
+        return ext.furthest_point_sampling(xyz.contiguous(), m)
     x = np.ascontiguousarray(xyz.detach().cpu().to(torch.float32).numpy())
     B, N, _ = x.shape
     out = np.zeros((B, m), dtype=np.int32)
@@ -54,7 +62,12 @@ def fps(xyz: torch.Tensor, m: int) -> torch.Tensor:
 
 def knn(query: torch.Tensor, ref: torch.Tensor, k: int, return_d2: bool = False):
     """model/utils.py:39-55 + argsort()[:, :, :k] (encoder/blocks.py:101-102) -> (B, M, k) int32,
-    ties resolved lowest-index-first."""
+    ties resolved lowest-index-first. CUDA tensors (GPU timing of the reference op chain only): the reference's own torch
+    formula, materialising [B, M, N, 3] and sorting every row."""
+    if query.is_cuda:
+        d2 = torch.sum((query[:, :, None] - ref[:, None]) ** 2, dim=-1)
+        idx = d2.argsort()[:, :, :k]
+        return (idx, torch.gather(d2, 2, idx)) if return_d2 else idx
     q = np.ascontiguousarray(query.detach().cpu().to(torch.float32).numpy())
     r = np.ascontiguousarray(ref.detach().cpu().to(torch.float32).numpy())
     B, M, _ = q.shape
@@ -184,7 +197,7 @@ def transformer_block(sd, p, xyz, feats, k, pos_only=False, group_all=False, tra
     B, n, _ = xyz.shape
     with torch.no_grad():
         if group_all:
-            idx = torch.arange(n).view(1, 1, n).expand(B, n, n)
+            idx = torch.arange(n, device=xyz.device).view(1, 1, n).expand(B, n, n)
         elif knn_override is not None:
             idx = knn_override
         else:
@@ -289,7 +302,7 @@ def cross_transformer_block(sd, p, xyz_q, z, anchors, anchor_feats, nneigh):
     vv = torch.cat([index_points(_lin(sd, p + ".w_vs", anchor_feats, bias=False), idx), vg], dim=2)
     rel = xyz_q[:, :, None] - index_points(anchors, idx)
     pos = _mlp2(sd, p + ".fc_delta", rel)
-    pos = torch.cat([pos, torch.zeros(B, Q, 1, pos.shape[-1], dtype=pos.dtype)], dim=2)
+    pos = torch.cat([pos, torch.zeros(B, Q, 1, pos.shape[-1], dtype=pos.dtype, device=pos.device)], dim=2)
     attn = F.softmax(_mlp2(sd, p + ".fc_gamma", q - kk + pos), dim=-2)
     return (attn * (vv + pos)).sum(dim=2)
 

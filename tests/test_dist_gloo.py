@@ -4,6 +4,7 @@ broadcast_parameters, and the contiguous batch sharding."""
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as td
@@ -88,6 +89,53 @@ def test_query_sharded_decode_world2():
     for rank, out, seen in res:
         assert torch.equal(out, want)          # every rank ends with all queries, in order
         assert seen == [4]                     # ... having decoded only its (padded) slice
+
+
+def _net():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Linear(5, 6), torch.nn.BatchNorm1d(6), torch.nn.ReLU(), torch.nn.Linear(6, 2))
+
+
+def _syncbn_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    model = nd.convert_sync_batchnorm(_net())
+    model.train()
+    x = torch.randn(12, 5, generator=torch.Generator().manual_seed(9))
+    mine = nd.shard_batch({"x": x})["x"]
+    out = model(mine)
+    out.pow(2).mean().backward()
+    nd.allreduce_gradients(model)
+    # numpy payloads are pickled by value (torch tensors travel as shared-memory handles that die with the worker)
+    q.put((rank, out.detach().numpy(), {k: v.grad.numpy() for k, v in model.named_parameters()},
+           {k: v.numpy() for k, v in model.named_buffers()}, list(model.state_dict().keys())))
+    td.destroy_process_group()
+
+
+def test_syncbn_reproduces_the_single_process_batch_world2():
+    """SURVEY.md §8e optional syncbn mode: 2 ranks x 6 rows == 1 process x 12 rows (outputs, gradients, running stats)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _net()
+    ref.train()
+    x = torch.randn(12, 5, generator=torch.Generator().manual_seed(9))
+    out = ref(x)
+    out.pow(2).mean().backward()
+    torch.testing.assert_close(torch.from_numpy(np.concatenate([res[0][1], res[1][1]])), out.detach(), atol=1e-5, rtol=1e-5)
+    for rank, _, grads, bufs, keys in res:
+        assert keys == list(ref.state_dict().keys())
+        for k, v in ref.named_parameters():
+            torch.testing.assert_close(torch.from_numpy(grads[k]), v.grad, atol=1e-5, rtol=1e-4)
+        for k, v in ref.named_buffers():
+            torch.testing.assert_close(torch.from_numpy(bufs[k]), v, atol=1e-6, rtol=1e-5)
 
 
 def test_inactive_without_process_group():
