@@ -216,16 +216,25 @@ fused_mlp_tc_kernel(const nsdp_mlp_args a, const unsigned char *__restrict__ pac
         const int col0 = c * CW + p * CPT;
 #pragma unroll
         for (int j = 0; j < CPT; j += 8) {
+          // 128-bit loads: the (warp-uniform) weight reads of this layer are LSU-issue bound, not latency bound
           float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int n = col0 + j + u;
-            float s = bias[n];
-#pragma unroll
-            for (int ci = 0; ci < 4; ++ci)
-              if (ci < Cin) s = fmaf(xin[ci], __ldg(a.w_in_t + (size_t)ci * W + n), s);
-            v[u] = fmaxf(s, 0.f);
+          {
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + col0 + j);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias + col0 + j + 4);
+            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
           }
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            if (ci < Cin) {
+              const float4 w0 = ldg4(a.w_in_t + (size_t)ci * W + col0 + j);
+              const float4 w1 = ldg4(a.w_in_t + (size_t)ci * W + col0 + j + 4);
+              const float xv = xin[ci];
+              v[0] = fmaf(xv, w0.x, v[0]); v[1] = fmaf(xv, w0.y, v[1]); v[2] = fmaf(xv, w0.z, v[2]); v[3] = fmaf(xv, w0.w, v[3]);
+              v[4] = fmaf(xv, w1.x, v[4]); v[5] = fmaf(xv, w1.y, v[5]); v[6] = fmaf(xv, w1.z, v[6]); v[7] = fmaf(xv, w1.w, v[7]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
           store_split8(X_hi, X_lo, r, col0 + j, v);
         }
         chunk_done(c);
@@ -246,9 +255,12 @@ fused_mlp_tc_kernel(const nsdp_mlp_args a, const unsigned char *__restrict__ pac
             tmem_ldn<CPT>(acc + col0, v);
 #pragma unroll
             for (int j = 0; j < CPT; j += 8) {
+              const float4 b0 = *reinterpret_cast<const float4 *>(bl + col0 + j);
+              const float4 b1 = *reinterpret_cast<const float4 *>(bl + col0 + j + 4);
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) x[u] = fmaxf(v[j + u] + bl[col0 + j + u], 0.f);
+              for (int u = 0; u < 8; ++u) x[u] = fmaxf(v[j + u] + bv[u], 0.f);
               store_split8(X_hi, X_lo, r, col0 + j, x);
             }
             chunk_done(c);

@@ -9,6 +9,9 @@
 //     init, fc_c[0], { fc_0[i], fc_c[i+1], fc_1[i] } for each block i.
 // fc_c[i+1] only needs `lat`, so it is issued right after fc_0[i] and runs on the tensor core while the workers are
 // busy turning acc1 into relu(h).
+// The relu(net) / relu(h) operand is handed over in four 32-column chunks (x_ready[c]): the k-steps of the next GEMM
+// that only need chunk c are issued while the workers are still converting chunks c+1.. (the scheme of
+// fused_mlp_tc.cu; the source accumulator and the destination accumulator of such a pair are always different).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -27,6 +30,9 @@ constexpr int THREADS = (2 + WORKER_WARPS) * 32;
 constexpr int MAX_BLOCKS = 8;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t ACC1_COL = 128;
+constexpr int XCH = 4;                    // chunks of the X operand handoff
+constexpr int XCW = H / XCH;              // 32 columns = 2 k-steps per chunk
+constexpr int XKPC = XCW / 16;
 
 template <int CP_>
 struct Cfg {
@@ -115,7 +121,8 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
   float4 *part = reinterpret_cast<float4 *>(smem + C::OFF_PART);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
   uint64_t *full = bars, *empty = bars + STAGES, *a_ready = bars + 2 * STAGES, *acc_done = a_ready + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+  uint64_t *x_ready = acc_done + 1;   // [XCH]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_ready + XCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = a.n_blocks, Cin = a.C, O = a.O;
@@ -145,6 +152,7 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
     }
     mbar_init(a_ready, WORKER_WARPS);
     mbar_init(acc_done, 1);
+    for (int c = 0; c < XCH; ++c) mbar_init(&x_ready[c], WORKER_WARPS);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -180,10 +188,10 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
       const uint64_t lhi = smem_desc(smem_u32(L_hi), lbo_a, 128), llo = smem_desc(smem_u32(L_lo), lbo_a, 128);
       const uint64_t xhi = smem_desc(smem_u32(X_hi), lbo_a, 128), xlo = smem_desc(smem_u32(X_lo), lbo_a, 128);
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
-      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
-      // one GEMM: A (hi/lo descriptors, ksteps) x next `ksteps` weight stages -> tmem column `col`
-      auto gemm = [&](uint64_t a_hi, uint64_t a_lo, int ksteps, uint32_t col, bool fresh) {
-        for (int ks = 0; ks < ksteps; ++ks) {
+      uint32_t slot = 0, slot_phase = 0, ready_phase = 0, x_phase = 0;
+      // one GEMM: A (hi/lo descriptors, k-steps [ks0, ks1)) x the next weight stages -> tmem column `col`
+      auto gemm_part = [&](uint64_t a_hi, uint64_t a_lo, int ks0, int ks1, uint32_t col, bool fresh) {
+        for (int ks = ks0; ks < ks1; ++ks) {
           mbar_wait(&full[slot], slot_phase, err);
           tc_fence_after();
           if (elect_one()) {
@@ -196,6 +204,18 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
           }
           if (++slot == STAGES) { slot = 0; slot_phase ^= 1; }
         }
+      };
+      auto gemm = [&](uint64_t a_hi, uint64_t a_lo, int ksteps, uint32_t col, bool fresh) {
+        gemm_part(a_hi, a_lo, 0, ksteps, col, fresh);
+      };
+      // X-operand GEMM, issued chunk by chunk as the workers hand the operand columns over
+      auto gemm_x = [&](uint32_t col, bool fresh) {
+        for (int c = 0; c < XCH; ++c) {
+          mbar_wait(&x_ready[c], x_phase, err);
+          tc_fence_after();
+          gemm_part(xhi, xlo, c * XKPC, (c + 1) * XKPC, col, fresh);
+        }
+        x_phase ^= 1;
       };
       auto commit_acc = [&]() {
         if (elect_one()) mma_commit(acc_done);
@@ -211,12 +231,10 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
         if (nb > 0) gemm(lhi, llo, C::KS_C, 0, false);  // fc_c[0]
         commit_acc();
         for (int i = 0; i < nb; ++i) {
-          wait_ready();                                 // x = relu(net + bsum_i)
-          gemm(xhi, xlo, KS_H, ACC1_COL, true);         // fc_0[i] -> acc1
+          gemm_x(ACC1_COL, true);                       // fc_0[i] -> acc1, chunks of x = relu(net + bsum_i) as they land
           commit_acc();
           if (i + 1 < nb) gemm(lhi, llo, C::KS_C, 0, false);  // fc_c[i+1] -> acc0 while the workers build y
-          wait_ready();                                 // y = relu(h + b0_i)
-          gemm(xhi, xlo, KS_H, 0, false);               // fc_1[i] -> acc0
+          gemm_x(0, false);                             // fc_1[i] -> acc0, chunks of y = relu(h + b0_i)
           commit_acc();
         }
       }
@@ -232,10 +250,12 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
     constexpr int XPT = H / 2;       // hidden columns per thread
     const int xb = half * XPT;
 
-    // acc (TMEM column base `col`) + bias -> relu -> bf16 hi/lo X operand
+    // acc (TMEM column base `col`) + bias -> relu -> bf16 hi/lo X operand, chunk by chunk: this warp converts columns
+    // [c*XCW + half*16, +16) of chunk c and signals x_ready[c]
     auto to_x = [&](uint32_t col, const float *bias) {
 #pragma unroll 1
-      for (int k0 = xb; k0 < xb + XPT; k0 += 16) {
+      for (int c = 0; c < XCH; ++c) {
+        const int k0 = c * XCW + half * (XCW / 2);
         float v[16];
         tmem_ld16(trow + col + k0, v);
 #pragma unroll
@@ -252,11 +272,11 @@ resnet_tail_tc_kernel(const nsdp_tail_args a, const unsigned char *__restrict__ 
           *reinterpret_cast<uint4 *>(X_hi + off) = hi;
           *reinterpret_cast<uint4 *>(X_lo + off) = lo;
         }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_ready[c]);
       }
-      tc_fence_before();
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
     };
     auto wait_acc = [&]() {
       mbar_wait(acc_done, done_phase, err);
