@@ -34,6 +34,7 @@ import torch  # noqa: E402
 
 B_PER_GPU, N_SURF, N_QUERY = 8, 4096, 50000
 METRIC = "query-points/sec (TDNet fwd+bwd, 50k queries/shape)"
+METRIC_FWD = "query-points/sec (TDNet forward only, eval mode, 50k queries/shape)"
 UNIT = "query-points/s"
 WORKLOAD = "configs[1]: forward-deformation TDNet, batch 8 shapes x 4096 surface pts x 50k spatial queries per GPU, " \
            "fwd+bwd training step (Adam)"
@@ -152,7 +153,7 @@ def cpu_reference_run(steps: int, warmup: int, shapes_per_step: int = 1, max_sec
                       f"torch CPU fp32 ({dt / max(done, 1):.2f} s/step)"}, dt / max(done, 1), done
 
 
-def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU):
+def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU, forward_only: bool = False):
     """NOT the contract's reference arm (that one is the CPU run below): the same restatement of the reference's op chain
     executed as PyTorch eager ops on cuda:0 (TF32 off; FPS = the reference's own CUDA kernel from oracle/_ref; k-NN = the
     reference's square_distance + argsort) — the "reference on 1 GPU" number BASELINE.json's >= 10x target is stated
@@ -172,7 +173,7 @@ def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU)
     opt = torch.optim.Adam(params, lr=5e-4)
     batch = {k: v.to(dev) for k, v in synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234).items()}
 
-    def step():
+    def train_step():
         opt.zero_grad()
         pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
                                  training=True)
@@ -181,6 +182,11 @@ def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU)
         opt.step()
         return loss.item()
 
+    def eval_forward():
+        with torch.no_grad():
+            return orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False)
+
+    step = eval_forward if forward_only else train_step
     for _ in range(max(warmup, 1)):
         step()
     torch.cuda.synchronize()
@@ -199,8 +205,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     if args.ref_device == "cuda":
-        qps, ms, gib = gpu_reference_run(args.steps, args.warmup)
-        emit_line({"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        qps, ms, gib = gpu_reference_run(args.steps, args.warmup, forward_only=args.forward_only)
+        emit_line({"impl": "reference", "metric": METRIC_FWD if args.forward_only else METRIC, "value": qps, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                    "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                    "vs_baseline": None, "dtype": "f32 (TF32 off)", "data": "synthetic",
                    "config": {"workload": WORKLOAD, "peak_memory_gib": gib,
@@ -236,6 +242,40 @@ def profile_kernels(step_fn, steps: int = 2):
     ops.TIMING = False
     summary = ops.timing_summary(reset=True)
     return summary, a.elapsed_time(b) / steps, steps
+
+
+def run_ours_forward_only(args):
+    """Informational (`--forward-only`): configs[1] as BASELINE.json words it — the eval-mode FORWARD of the TDNet through
+    the public `model(points, surface)` call, batch resident in HBM, CUDA events, L2 flushed between calls."""
+    from nsdp_b200 import ops, synth
+    from nsdp_b200.model import build_model
+    dev = torch.device("cuda", 0)
+    cfg = synth.make_config("forward")
+    model, *_ = build_model(cfg, device=dev)
+    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(synth.named_state_dict(schema, seed=0))
+    model.eval()
+    batch = {k: v.to(dev) for k, v in synth.forward_batch(B_PER_GPU, N_SURF, N_QUERY, seed=1234).items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms, before = 0.0, 0
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3) + args.steps):
+            if i == max(args.warmup, 3):
+                before = ops.LAUNCHES
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model(batch["space_samples_src"], batch["surface_samples_inputs"])
+            b.record()
+            b.synchronize()
+            if i >= max(args.warmup, 3):
+                ms += a.elapsed_time(b)
+    emit_line({"metric": METRIC_FWD, "value": B_PER_GPU * N_QUERY * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)",
+               "data": "synthetic", "gpu_launches": ops.LAUNCHES - before,
+               "config": {"workload": WORKLOAD.replace("fwd+bwd training step (Adam)", "eval-mode forward only"),
+                          "l2": "256 MiB buffer zeroed between calls"}})
 
 
 def run_ours(args):
@@ -383,6 +423,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="informational: eval-mode forward instead of the training step (ours, or --ref-device cuda)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="with --impl reference: cuda = the reference op chain as PyTorch eager on one GPU (informational)")
     args = ap.parse_args()
@@ -391,6 +433,8 @@ def main():
     with contextlib.redirect_stdout(sys.stderr):
         if args.impl == "reference":
             run_reference_arm(args)
+        elif args.forward_only:
+            run_ours_forward_only(args)
         else:
             run_ours(args)
 

@@ -27,17 +27,18 @@ template <int W_>
 struct Cfg {
   static constexpr int W = W_;
   static constexpr int KS = W / 16;                    // k-steps (= weight stages) per layer
-  static constexpr int NWQ = W >= 64 ? 4 : 2;          // worker warps per TMEM lane quarter
-  static constexpr int CPT = W >= 256 ? 16 : 8;        // accumulator columns per thread per chunk
+  // narrow widths are bound by the per-layer handoff latency: small CTAs (few worker warps), many of them per SM
+  static constexpr int NWQ = W >= 128 ? 4 : (W >= 64 ? 2 : 1);   // worker warps per TMEM lane quarter
+  static constexpr int CPT = (W >= 256 || W <= 32) ? 16 : 8;     // accumulator columns per thread per chunk
   static constexpr int CW = NWQ * CPT;                 // chunk width (columns)
   static constexpr int NCH = W / CW;                   // chunks per layer
   static constexpr int KPC = CW / 16;                  // k-steps per chunk
   static constexpr int WORKERS = 4 * NWQ;              // worker warps
   static constexpr int THREADS = (2 + WORKERS) * 32;   // + weight producer warp + MMA issuing warp
-  static constexpr int MIN_CTAS = W >= 256 ? 1 : (W >= 64 ? 2 : 4);   // co-resident CTAs hide the per-layer handoff
+  static constexpr int MIN_CTAS = W >= 256 ? 1 : (W >= 128 ? 2 : (W >= 64 ? 4 : 6));   // co-resident CTAs hide the handoff
   static constexpr int SLAB = W * 16 * 2;              // [W x 16] bf16
   static constexpr int STAGE_BYTES = 2 * SLAB;         // hi + lo
-  static constexpr int STAGES = W >= 256 ? 5 : (W >= 128 ? 4 : 8);   // W = 128: two CTAs of 108 KB share an SM
+  static constexpr int STAGES = W >= 256 ? 5 : (W >= 64 ? 4 : 8);    // W = 128: two CTAs of 108 KB share an SM; W = 64: four of 53 KB
   static constexpr uint32_t TMEM_COLS = 2 * W < 32 ? 32 : 2 * W;
   static constexpr int A_HALF = 128 * W * 2;
   static constexpr int OFF_X = 0;

@@ -25,21 +25,3 @@ def mlp_forward(x, w_in, b_in, w_h, b_h, w_out, b_out, dtype=np.float64):
         h = h @ np.asarray(w_h[l], dtype=dtype).T + np.asarray(b_h[l], dtype=dtype)
         h = np.maximum(h, 0)
     return h @ np.asarray(w_out, dtype=dtype).T + np.asarray(b_out, dtype=dtype)
-
-
-def synth_mlp(W: int, n_hidden: int, Cin: int = 3, O: int = 3, seed: int = 0):
-    """Seeded nn.Linear-style weights (uniform +-1/sqrt(fan_in), as torch's default init) as float32 numpy arrays."""
-    rng = np.random.default_rng(seed)
-
-    def lin(o, i):
-        b = 1.0 / np.sqrt(i)
-        return (rng.uniform(-b, b, size=(o, i)).astype(np.float32), rng.uniform(-b, b, size=(o,)).astype(np.float32))
-
-    w_in, b_in = lin(W, Cin)
-    hs = [lin(W, W) for _ in range(n_hidden)]
-    w_h = np.stack([h[0] for h in hs]) if n_hidden else np.zeros((0, W, W), np.float32)
-    b_h = np.stack([h[1] for h in hs]) if n_hidden else np.zeros((0, W), np.float32)
-    # hidden layers are scaled up so that activations neither die nor blow up through 6 ReLU layers
-    w_h = (w_h * np.float32(2.4)).astype(np.float32)
-    w_out, b_out = lin(O, W)
-    return w_in, b_in, w_h, b_h, w_out, b_out

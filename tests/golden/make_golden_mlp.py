@@ -9,11 +9,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.mlp_oracle import synth_mlp  # noqa: E402
+from nsdp_b200 import synth  # noqa: E402
 
 out = {}
 for W, L in ((16, 2), (64, 6), (256, 6)):
-    w_in, b_in, w_h, b_h, w_out, b_out = synth_mlp(W, L, seed=W)
+    w_in, b_in, w_h, b_h, w_out, b_out = synth.mlp_weights(W, L, seed=W)
     layers = [torch.nn.Linear(3, W), torch.nn.ReLU()]
     for _ in range(L):
         layers += [torch.nn.Linear(W, W), torch.nn.ReLU()]

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from nsdp_b200 import ops
+from nsdp_b200 import ops, synth
 from oracle import mlp_oracle
 
 pytestmark = pytest.mark.gpu
@@ -13,7 +13,7 @@ DEV = "cuda:0"
 
 
 def _net(W, L, impl, Cin=3, O=3, seed=0):
-    w = mlp_oracle.synth_mlp(W, L, Cin=Cin, O=O, seed=seed)
+    w = synth.mlp_weights(W, L, Cin=Cin, O=O, seed=seed)
     net = ops.FusedMLP(*[torch.from_numpy(t).to(DEV) for t in w], impl=impl)
     return w, net
 

@@ -14,8 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from nsdp_b200 import ops
-from oracle import mlp_oracle   # seeded weights only (tools/ is not product code)
+from nsdp_b200 import ops, synth
 
 DEV = "cuda:0"
 R, L = int(os.environ.get("C4_ROWS", 1_000_000)), 6
@@ -42,7 +41,7 @@ xs = [(torch.rand(R, 3, generator=g) - 0.5).to(DEV) for _ in range(NBUF)]
 outs = [torch.empty(R, 3, device=DEV) for _ in range(NBUF)]
 rows = []
 for W in (16, 32, 64, 128, 256):
-    w = [torch.from_numpy(t).to(DEV) for t in mlp_oracle.synth_mlp(W, L, seed=W)]
+    w = [torch.from_numpy(t).to(DEV) for t in synth.mlp_weights(W, L, seed=W)]
     net = ops.FusedMLP(*w, impl=0)
     ms, p10, p90 = timed(lambda i: net(xs[i % NBUF], outs[i % NBUF]))
     w_in, b_in, w_h, b_h, w_out, b_out = w
