@@ -27,6 +27,10 @@ peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.absp
 def timed(fn, reps=30, warm=5):
     for i in range(warm):
         fn(i)
+    # at least ~0.3 s of timed work per configuration: short bursts sit on the power-state ramp of the box
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(0); b.record(); b.synchronize()
+    reps = max(reps, min(400, int(300.0 / max(a.elapsed_time(b), 1e-3))))
     ts = []
     for i in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
