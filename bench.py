@@ -296,7 +296,13 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         ndist.init_process_group("nccl")
 
-    cfg = synth.make_config("forward")
+    global B_PER_GPU, WORKLOAD
+    c3 = args.workload == "c3"
+    if c3:   # informational: BASELINE.json configs[2], the arbitrary-pose (FlowArbitrary) training step, 4 shapes per GPU
+        B_PER_GPU = 4
+        WORKLOAD = "configs[2]: arbitrary-pose FlowArbitrary (canonicalise + deform TDNets), batch 4 shapes x 4096 surface " \
+                   "pts x 50k spatial queries per GPU (global batch 32 on 8 GPUs), fwd+bwd training step (Adam)"
+    cfg = synth.make_config("arbitrary" if c3 else "forward")
     model, train_on_batch, _, _ = build_model(cfg, device=dev)
     schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
     model.load_state_dict(synth.named_state_dict(schema, seed=0))
@@ -364,8 +370,8 @@ def run_ours(args):
         nq = B_PER_GPU * N_QUERY
         flops = {"vattn_bwd": VATTN_DEC_BWD_FLOP_PER_QUERY * nq, "vattn_fwd": VATTN_DEC_FWD_FLOP_PER_QUERY * nq}
         top = max(summary.items(), key=lambda kv: kv[1]["ms"])
-        dec_bwd = next(v for k, v in summary.items() if k.startswith("vattn_bwd_D200"))
-        dec_fwd = next(v for k, v in summary.items() if k.startswith("vattn_fwd_D200"))
+        dec_bwd = summary[f"vattn_bwd_D200_K7_M{N_QUERY}"]
+        dec_fwd = summary[f"vattn_fwd_D200_K7_M{N_QUERY}"]
         bwd_ms = dec_bwd["ms"] / dec_bwd["calls"]
         fwd_ms = dec_fwd["ms"] / dec_fwd["calls"]
         achieved = flops["vattn_bwd"] / (bwd_ms * 1e-3) / 1e12
@@ -392,18 +398,20 @@ def run_ours(args):
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,
                                "share_of_step": dec_fwd["ms"] / prof_steps / prof_step_ms},
                 "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summary.items())}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not c3:
             cpu, _, _ = cpu_reference_run(steps=2, warmup=1, max_seconds=60.0)
     if world > 1:
         td.barrier()
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC.replace("TDNet", "FlowArbitrary, 3 TDNet passes,") if c3 else METRIC, "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "surface_pts": N_SURF, "queries": N_QUERY,
                            "parallelism": f"dp{world}", "l2": "256 MiB buffer zeroed between steps (outside the event pairs)",
-                           "bn": "local per-rank batch statistics", "wall_s": wall},
+                           "bn": ("global-batch statistics (syncbn)" if os.environ.get("NSDP_B200_SYNCBN", "0") == "1" and world > 1
+                                  else "local per-rank batch statistics"), "wall_s": wall},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms / args.steps},
@@ -423,6 +431,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the headline): forward-deformation TDNet, 8 shapes/GPU; c3 (informational): FlowArbitrary, "
+                         "4 shapes/GPU")
     ap.add_argument("--forward-only", action="store_true",
                     help="informational: eval-mode forward instead of the training step (ours, or --ref-device cuda)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
