@@ -246,6 +246,22 @@ size_t nsdp_fused_mlp_fwd_workspace_bytes(const nsdp_mlp_args *args);
 int nsdp_fused_mlp_fwd_f32(const nsdp_mlp_args *args, float *out /* (R,O) */, void *workspace, size_t workspace_bytes,
                            void *stream);
 
+/* Backward of nsdp_fused_mlp_fwd_f32 (recomputes the activations tile by tile; what autograd does to the same nn.Linear /
+ * ReLU stack). Gradient buffers have the layouts of the corresponding (transposed) forward arguments, ACCUMULATE and must
+ * be zero-filled on entry; d_x (R, Cin) is fully overwritten and may be NULL. tcgen05 kernel only (W in {16, 32, 64, 128,
+ * 256}, 1 <= n_hidden <= 7): the chain kernel stages the operand tiles of every layer (bf16 hi/lo) segment by segment and
+ * the split-K reduction kernel turns them into weight / bias gradients. */
+typedef struct {
+  float *d_x;
+  float *d_w_in_t, *d_b_in;
+  float *d_w_h_t, *d_b_h;
+  float *d_w_out_t, *d_b_out;
+} nsdp_mlp_grads;
+
+size_t nsdp_fused_mlp_bwd_workspace_bytes(const nsdp_mlp_args *args);
+int nsdp_fused_mlp_bwd_f32(const nsdp_mlp_args *args, const float *d_out /* (R,O) */, const nsdp_mlp_grads *grads,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
  * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.

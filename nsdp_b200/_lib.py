@@ -58,6 +58,10 @@ class MlpArgs(C.Structure):
     ]
 
 
+class MlpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_x", "d_w_in_t", "d_b_in", "d_w_h_t", "d_b_h", "d_w_out_t", "d_b_out")]
+
+
 # name -> (restype, argtypes); must list every symbol include/nsdp_b200.h declares
 # (tests/test_abi.py cross-checks this table against the header).
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -88,6 +92,8 @@ SIGNATURES = {
     "nsdp_resnet_tail_bwd_f32": (_I, [C.POINTER(TailArgs), _P, C.POINTER(TailGrads), _P, _SZ, _P]),
     "nsdp_fused_mlp_fwd_workspace_bytes": (_SZ, [C.POINTER(MlpArgs)]),
     "nsdp_fused_mlp_fwd_f32": (_I, [C.POINTER(MlpArgs), _P, _P, _SZ, _P]),
+    "nsdp_fused_mlp_bwd_workspace_bytes": (_SZ, [C.POINTER(MlpArgs)]),
+    "nsdp_fused_mlp_bwd_f32": (_I, [C.POINTER(MlpArgs), _P, C.POINTER(MlpGrads), _P, _SZ, _P]),
     "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 

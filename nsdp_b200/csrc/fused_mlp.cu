@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(THREADS) fused_mlp_fwd_kernel(const nsdp_mlp_a
 
 }  // namespace mlp
 
+size_t mlp_bwd_tc_workspace_bytes(const nsdp_mlp_args *a);
+int mlp_bwd_tc_dispatch(const nsdp_mlp_args *a, const float *dout, const nsdp_mlp_grads *g, void *workspace, size_t ws_bytes,
+                        cudaStream_t st);
 size_t mlp_tc_workspace_bytes(const nsdp_mlp_args *a);
 int mlp_tc_dispatch(const nsdp_mlp_args *a, float *out, void *workspace, size_t ws_bytes, cudaStream_t st, bool *handled);
 }  // namespace nsdp
@@ -95,4 +98,18 @@ extern "C" int nsdp_fused_mlp_fwd_f32(const nsdp_mlp_args *a, float *out, void *
   const long long tiles = ceil_div((long long)a->R, (long long)mlp::ROWS);
   mlp::fused_mlp_fwd_kernel<<<(unsigned)tiles, mlp::THREADS, 0, (cudaStream_t)stream>>>(*a, out);
   return check_launch();
+}
+
+extern "C" size_t nsdp_fused_mlp_bwd_workspace_bytes(const nsdp_mlp_args *a) {
+  if (mlp_validate(a) != NSDP_OK) return 0;
+  return nsdp::mlp_bwd_tc_workspace_bytes(a);
+}
+
+extern "C" int nsdp_fused_mlp_bwd_f32(const nsdp_mlp_args *a, const float *d_out, const nsdp_mlp_grads *g, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+  int rc = mlp_validate(a);
+  if (rc != NSDP_OK) return rc;
+  if (!d_out || !g || !g->d_w_in_t || !g->d_b_in || !g->d_w_out_t || !g->d_b_out || !g->d_w_h_t || !g->d_b_h)
+    return NSDP_ERR_INVALID_ARGUMENT;
+  return nsdp::mlp_bwd_tc_dispatch(a, d_out, g, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MlpArgs, TailArgs, TailGrads, VattnArgs, VattnGrads, check
+from ._lib import MlpArgs, MlpGrads, TailArgs, TailGrads, VattnArgs, VattnGrads, check
 
 LAUNCHES = 0  # number of libnsdp_b200 kernel-launching calls made (bench.py reports it)
 
@@ -443,3 +443,64 @@ class FusedMLP:
             self._packed = bool(ws_bytes)
         _count()
         return out
+
+
+class _FusedMLPFn(torch.autograd.Function):
+    """Differentiable form of the fused MLP: forward = nsdp_fused_mlp_fwd_f32, backward = nsdp_fused_mlp_bwd_f32 (which
+    recomputes the activations on chip). Weights are taken TRANSPOSED (w_in_t (Cin,W), w_h_t (L,W,W), w_out_t (W,O)) so
+    that the gradient buffers the kernel fills are the autograd results as they are."""
+
+    @staticmethod
+    def forward(ctx, x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out):
+        for n, t in dict(x=x, w_in_t=w_in_t, b_in=b_in, w_h_t=w_h_t, b_h=b_h, w_out_t=w_out_t, b_out=b_out).items():
+            _chk_f32(n, t)
+        a = _mlp_args(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out)
+        out = torch.empty((a.R, a.O), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            ws_bytes = L.nsdp_fused_mlp_fwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
+            with _timed("fused_mlp_fwd"):
+                check(L.nsdp_fused_mlp_fwd_f32(C.byref(a), out.data_ptr(), _p(ws), ws_bytes, _stream()), "nsdp_fused_mlp_fwd_f32")
+        _count()
+        ctx.save_for_backward(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        a = _mlp_args(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out)
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        grads = [torch.zeros_like(t) for t in (w_in_t, b_in, w_h_t, b_h, w_out_t, b_out)]
+        gs = MlpGrads()
+        gs.d_x = _p(d_x)
+        for n, t in zip(("d_w_in_t", "d_b_in", "d_w_h_t", "d_b_h", "d_w_out_t", "d_b_out"), grads):
+            setattr(gs, n, _p(t))
+        L = _lib.lib()
+        with torch.cuda.device(d_out.device):
+            ws_bytes = L.nsdp_fused_mlp_bwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_out.device) if ws_bytes else None
+            with _timed("fused_mlp_bwd"):
+                check(L.nsdp_fused_mlp_bwd_f32(C.byref(a), d_out.data_ptr(), C.byref(gs), _p(ws), ws_bytes, _stream()),
+                      "nsdp_fused_mlp_bwd_f32")
+        _count()
+        return (d_x, *grads)
+
+
+def _mlp_args(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out) -> MlpArgs:
+    a = MlpArgs()
+    a.x, a.w_in_t, a.b_in = _p(x), _p(w_in_t), _p(b_in)
+    a.w_h_t, a.b_h, a.w_out_t, a.b_out = _p(w_h_t), _p(b_h), _p(w_out_t), _p(b_out)
+    a.R, a.Cin = x.shape
+    a.W, a.O = w_out_t.shape
+    a.n_hidden = w_h_t.shape[0]
+    a.impl = 0
+    a.reuse_packed = 0
+    return a
+
+
+def fused_mlp(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out):
+    """Differentiable fused MLP over rows (R, Cin) -> (R, O) with TRANSPOSED weights (see nsdp_mlp_args); training-time
+    counterpart of `FusedMLP`."""
+    return _FusedMLPFn.apply(x, w_in_t, b_in, w_h_t, b_h, w_out_t, b_out)

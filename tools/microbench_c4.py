@@ -62,6 +62,32 @@ for W in (16, 32, 64, 128, 256):
     torch.backends.cuda.matmul.allow_tf32 = True
     ms_tf32, _, _ = timed(eager, reps=10, warm=3)
     torch.backends.cuda.matmul.allow_tf32 = False
+    # training step of the same stack: forward + backward (weight, bias and coordinate gradients) through ops.fused_mlp
+    params = [w_in.t().contiguous(), b_in, w_h.transpose(1, 2).contiguous(), b_h, w_out.t().contiguous(), b_out]
+    params = [p_.requires_grad_(True) for p_ in params]
+    xg = [x_.clone().requires_grad_(True) for x_ in xs[:2]]
+    d_o = torch.randn(R, 3, device=DEV)
+
+    def ours_train(i):
+        for p_ in params:
+            p_.grad = None
+        xg[i % 2].grad = None
+        ops.fused_mlp(xg[i % 2], *params).backward(d_o)
+
+    lin = [w_in.clone().requires_grad_(True), b_in.clone().requires_grad_(True), w_h.clone().requires_grad_(True),
+           b_h.clone().requires_grad_(True), w_out.clone().requires_grad_(True), b_out.clone().requires_grad_(True)]
+
+    def eager_train(i):
+        for p_ in lin:
+            p_.grad = None
+        xg[i % 2].grad = None
+        h = torch.relu(torch.addmm(lin[1], xg[i % 2], lin[0].t()))
+        for l in range(L):
+            h = torch.relu(torch.addmm(lin[3][l], h, lin[2][l].t()))
+        torch.addmm(lin[5], h, lin[4].t()).backward(d_o)
+
+    ms_train, _, _ = timed(ours_train, reps=10, warm=3)
+    ms_train_eager, _, _ = timed(eager_train, reps=5, warm=2)
     flop = 2.0 * (3 * W + L * W * W + W * 3)
     tfl = R * flop / (ms * 1e-3) / 1e12
     gbs = R * 24 / (ms * 1e-3) / 1e9
@@ -75,6 +101,9 @@ for W in (16, 32, 64, 128, 256):
         "frac_tensor_peak_executed": 3 * R * 2.0 * L * W * W / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
         "torch_eager_fp32_ms": ms_eager, "torch_eager_tf32_ms": ms_tf32, "speedup_vs_eager_fp32": ms_eager / ms,
         "speedup_vs_eager_tf32": ms_tf32 / ms, "max_abs_diff_vs_eager_fp32": err,
+        "fwd_bwd_ms": ms_train, "fwd_bwd_points_per_s": R / (ms_train * 1e-3),
+        "fwd_bwd_algorithmic_tflops": 3 * R * flop / (ms_train * 1e-3) / 1e12,
+        "torch_eager_fp32_fwd_bwd_ms": ms_train_eager, "fwd_bwd_speedup_vs_eager_fp32": ms_train_eager / ms_train,
     })
     print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
 print(json.dumps({"config": "configs[3]: 1M query points, 3 -> W, 6 x (W -> W), W -> 3, fp32 in/out, bf16x3 tcgen05",
