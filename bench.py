@@ -278,6 +278,38 @@ def run_ours_forward_only(args):
                           "l2": "256 MiB buffer zeroed between calls"}})
 
 
+def decoder_mlp_microbench(dev, peaks):
+    """BASELINE.json's second metric ("decoder HBM GB/s", configs[3]): 1M query points through the fused 256-wide 8-layer
+    MLP (ops.FusedMLP -> nsdp_fused_mlp_fwd_f32), CUDA events per call, inputs rotating through > L2. Informational
+    sub-object of the bench line; the full width sweep is tools/microbench_c4.py."""
+    from nsdp_b200 import ops, synth
+    R, W, L, nbuf = 1_000_000, 256, 6, 12
+    net = ops.FusedMLP(*[torch.from_numpy(t).to(dev) for t in synth.mlp_weights(W, L, seed=W)])
+    g = torch.Generator().manual_seed(5)
+    xs = [(torch.rand(R, 3, generator=g) - 0.5).to(dev) for _ in range(nbuf)]
+    outs = [torch.empty(R, 3, device=dev) for _ in range(nbuf)]
+    for i in range(5):
+        net(xs[i % nbuf], outs[i % nbuf])
+    ts = []
+    for i in range(40):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        net(xs[i % nbuf], outs[i % nbuf])
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    flop = 2.0 * (3 * W + L * W * W + W * 3)
+    executed = 3 * R * 2.0 * L * W * W / (ms * 1e-3) / 1e12
+    return {"workload": "configs[3]: 1M query points x (3 -> 256, 6 x (256 -> 256), 256 -> 3), fp32 in/out",
+            "ms": ms, "ms_p10": ts[len(ts) // 10], "points_per_s": R / (ms * 1e-3),
+            "algorithmic_tflops": R * flop / (ms * 1e-3) / 1e12, "executed_mma_tflops": executed,
+            "executed_frac_of_bf16_peak": executed / peaks["bf16_tflops"],
+            "hbm_gbs": R * 24 / (ms * 1e-3) / 1e9, "hbm_frac": R * 24 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "bound": "tensor (32 896 FLOP per HBM byte; the activations never leave the SM)"}
+
+
 def run_ours(args):
     import torch.distributed as td
 
@@ -398,6 +430,11 @@ def run_ours(args):
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,
                                "share_of_step": dec_fwd["ms"] / prof_steps / prof_step_ms},
                 "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summary.items())}}
+        if world == 1 and not c3:
+            try:
+                roof["decoder_mlp"] = decoder_mlp_microbench(dev, peaks)
+            except Exception as exc:   # informational only: never lose the bench line over it
+                print(f"[bench] decoder MLP microbenchmark skipped: {exc}", file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline and not c3:
             cpu, _, _ = cpu_reference_run(steps=2, warmup=1, max_seconds=60.0)
     if world > 1:
