@@ -8,7 +8,10 @@ model files) `import pointnet2_ops_lib.pointnet2_ops.pointnet2_utils` (train.py:
 Those names are pre-bound in sys.modules to the nsdp_b200 mirrors, so the script's own `model/` directory is never
 imported. Under torchrun every rank pins itself to its GPU via CUDA_VISIBLE_DEVICES so that the script's hard-wired
 `cuda:0` (train.py:74-77) is the rank's device; build_model() then joins the process group and the train_on_batch_*
-functions all-reduce gradients (nsdp_b200/dist.py).
+functions all-reduce gradients (nsdp_b200/dist.py). For `train.py` every rank also gets its own `--seed` (base + rank:
+the script builds its own shuffled DataLoader without a sampler, train.py:121-127, so distinct seeds give distinct
+batches) and ranks > 0 their own `experiment.out_dir` (a rank-suffixed copy of the YAML config), otherwise all ranks
+would race on the same `model_%05d` / `opt_%05d` files (utils/checkpoints.py:35-43).
 """
 from __future__ import annotations
 
@@ -35,6 +38,40 @@ def install_aliases() -> None:
     sys.modules["pointnet2_ops_lib.pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
 
 
+def rewrite_argv_for_rank(argv, rank: int, world: int, scratch_dir: str):
+    """argv = [train.py, config.yaml, ...] -> the same with `--seed base+rank` and, for rank > 0, a copy of the config whose
+    `experiment.out_dir` is `<out_dir>/rank<r>`. Other scripts and single-process runs are returned unchanged."""
+    argv = list(argv)
+    if world <= 1 or not argv or os.path.basename(argv[0]) != "train.py":
+        return argv
+    base = 27                                            # train.py:45 default
+    if "--seed" in argv[:-1]:
+        i = argv.index("--seed")
+        base = int(argv[i + 1])
+        del argv[i:i + 2]
+    else:
+        for i, tok in enumerate(argv):
+            if tok.startswith("--seed="):
+                base = int(tok.split("=", 1)[1])
+                del argv[i]
+                break
+    argv += ["--seed", str(base + rank)]
+    if rank > 0:
+        pos = [i for i, tok in enumerate(argv[1:], 1) if not tok.startswith("-") and (i == 1 or not argv[i - 1].startswith("--"))]
+        if pos:
+            import yaml
+            ci = pos[0]
+            with open(argv[ci]) as f:
+                cfg = yaml.safe_load(f)
+            cfg["experiment"]["out_dir"] = os.path.join(str(cfg["experiment"]["out_dir"]), f"rank{rank}")
+            os.makedirs(scratch_dir, exist_ok=True)
+            out = os.path.join(scratch_dir, f"rank{rank}_" + os.path.basename(argv[ci]))
+            with open(out, "w") as f:
+                yaml.safe_dump(cfg, f)
+            argv[ci] = out
+    return argv
+
+
 def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
@@ -43,6 +80,8 @@ def main(argv=None) -> None:
     if local_rank is not None and "NSDP_B200_KEEP_VISIBLE" not in os.environ:
         os.environ["CUDA_VISIBLE_DEVICES"] = local_rank
     install_aliases()
+    argv = rewrite_argv_for_rank(argv, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                                 os.path.join(os.environ.get("TMPDIR", "/tmp"), f"nsdp_b200_launch_{os.getpid()}"))
     script = argv[0]
     sys.argv = argv
     sys.path.insert(0, os.path.dirname(os.path.abspath(script)))

@@ -23,3 +23,22 @@ def test_aliases_resolve_to_mirrors():
         for k in list(sys.modules):
             if k not in saved:
                 del sys.modules[k]
+
+
+def test_per_rank_seed_and_output_directory(tmp_path):
+    """Under torchrun every rank of an unchanged train.py gets a distinct --seed, and ranks > 0 a private out_dir
+    (design A)."""
+    import yaml
+    from nsdp_b200 import launch
+    cfg = tmp_path / "forward.yaml"
+    cfg.write_text(yaml.safe_dump({"experiment": {"out_dir": "/data/out", "name": "run"}, "model": {"type": "forward"}}))
+    argv = ["/repo/NSDP/train.py", str(cfg), "--num_workers", "4"]
+    assert launch.rewrite_argv_for_rank(argv, 0, 1, str(tmp_path)) == argv                       # single process: untouched
+    r0 = launch.rewrite_argv_for_rank(argv, 0, 8, str(tmp_path / "s"))
+    assert r0 == argv + ["--seed", "27"]                                                          # rank 0 keeps the config
+    r3 = launch.rewrite_argv_for_rank(argv + ["--seed", "100"], 3, 8, str(tmp_path / "s"))
+    assert r3[-2:] == ["--seed", "103"] and r3.count("--seed") == 1 and r3[2:4] == ["--num_workers", "4"]
+    got = yaml.safe_load(open(r3[1]))
+    assert got["experiment"] == {"out_dir": "/data/out/rank3", "name": "run"} and got["model"] == {"type": "forward"}
+    test_argv = ["/repo/NSDP/test.py", str(cfg)]
+    assert launch.rewrite_argv_for_rank(test_argv, 3, 8, str(tmp_path)) == test_argv              # only train.py writes checkpoints
