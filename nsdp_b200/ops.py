@@ -414,6 +414,19 @@ class FusedMLP:
         self._ws = None
         self._packed = False
 
+    def refresh(self, w_in=None, b_in=None, w_h=None, b_h=None, w_out=None, b_out=None) -> None:
+        """Call after the weights changed (optionally passing the new nn.Linear-layout tensors): the next call re-packs."""
+        if w_in is not None:
+            self.w_in_t = _chk_f32("w_in", w_in).t().contiguous()
+        if w_h is not None:
+            self.w_h_t = _chk_f32("w_h", w_h).transpose(1, 2).contiguous()
+        if w_out is not None:
+            self.w_out_t = _chk_f32("w_out", w_out).t().contiguous()
+        self.b_in = self.b_in if b_in is None else _chk_f32("b_in", b_in)
+        self.b_h = self.b_h if b_h is None else _chk_f32("b_h", b_h)
+        self.b_out = self.b_out if b_out is None else _chk_f32("b_out", b_out)
+        self._packed = False
+
     def _args(self, x: torch.Tensor) -> MlpArgs:
         a = MlpArgs()
         a.x, a.w_in_t, a.b_in = _p(x), _p(self.w_in_t), _p(self.b_in)
@@ -430,6 +443,8 @@ class FusedMLP:
         a = self._args(x)
         if out is None:
             out = torch.empty((a.R, a.O), dtype=torch.float32, device=x.device)
+        elif _chk_f32("out", out).shape != (a.R, a.O) or out.device != x.device:
+            raise RuntimeError(f"out must be a ({a.R}, {a.O}) tensor on {x.device}")
         L = _lib.lib()
         with torch.cuda.device(x.device):
             ws_bytes = L.nsdp_fused_mlp_fwd_workspace_bytes(C.byref(a))
