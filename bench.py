@@ -112,31 +112,81 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (restatement of the reference path) on the host cores
+# Reference arm: the UNMODIFIED reference model (baseline/_ref, see baseline/make_ref.py) through its own public API
+# (build_model / optimizer_factory / train_on_batch); the oracle port only if that copy is absent. Nothing here
+# imports nsdp_b200.model, nsdp_b200.ops or nsdp_b200.dist: under torchrun only rank 0 runs, without a process group.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, shapes_per_step: int = 1, max_seconds: float = 240.0):
-    from nsdp_b200 import synth
-    from nsdp_b200.model import build_model
-    from oracle import tdnet_oracle as orc
-
-    torch.set_num_threads(os.cpu_count() or 1)
+def _reference_api(device):
+    """-> (kind, step_fn_factory). kind "reference": baseline/_ref's own build_model + train_on_batch_with_cano;
+    kind "port": oracle/tdnet_oracle.py (restatement) with the state_dict schema from tests/golden."""
+    from nsdp_b200 import synth   # data + seeded weights only (pure numpy/torch, no kernels, no model code)
     cfg = synth.make_config("forward")
-    model, *_ = build_model(cfg)  # only used for the state_dict schema (CPU construction, no kernels run)
-    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
-    sd = synth.named_state_dict(schema, seed=0)
+    try:
+        from baseline import ref_loader
+        ref = ref_loader.load() if ref_loader.available() else None
+    except Exception as exc:
+        print(f"[bench] baseline/_ref not usable ({exc}); falling back to the oracle port", file=sys.stderr)
+        ref = None
+    if ref is not None:
+        model, train_on_batch, _, _ = ref.build_model(cfg, device=device)
+        schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+        model.load_state_dict(synth.named_state_dict(schema, seed=0))
+        model.train()
+        _, opt = ref.optimizer_factory(cfg["training"], model.parameters())
+
+        def make(batch, forward_only=False):
+            if forward_only:
+                model.eval()
+
+                def fwd():
+                    with torch.no_grad():
+                        return model(batch["space_samples_src"], batch["surface_samples_inputs"])
+                return fwd
+            return lambda: train_on_batch(model, opt, batch, cfg)
+        return "reference", make
+    from oracle import tdnet_oracle as orc
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")) as f:
+        schema = [(k, tuple(s)) for k, s in json.load(f)["forward"]]
+    sd = {k: v.to(device) for k, v in synth.named_state_dict(schema, seed=0).items()}
     params = [v.requires_grad_(True) for k, v in sd.items() if k.rsplit(".", 1)[-1] in ("weight", "bias")]
     opt = torch.optim.Adam(params, lr=5e-4)
-    batch = synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234)
 
-    def step():
-        opt.zero_grad()
-        pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
-                                 training=True)
-        loss = orc.l2_loss(pred, batch["space_samples_tgt"])
-        loss.backward()
-        opt.step()
-        return loss.item()
+    def make(batch, forward_only=False):
+        def train_step():
+            opt.zero_grad()
+            pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
+                                     training=True)
+            loss = orc.l2_loss(pred, batch["space_samples_tgt"])
+            loss.backward()
+            opt.step()
+            return loss.item()
 
+        def fwd():
+            with torch.no_grad():
+                return orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False)
+        return fwd if forward_only else train_step
+    return "port", make
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 150.0):
+    """The reference's training step on the host cores, all threads. Each step is a bounded SAMPLE of the workload: whole
+    shapes of 4096 surface points x 50 000 queries, as many per step (<= 8) as keep warmup + steps inside `budget_s` and
+    the ~4 GB of autograd state per shape inside the free host memory. Cost is linear in the number of shapes."""
+    from nsdp_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind, make = _reference_api("cpu")
+    probe = make(synth.forward_batch(1, N_SURF, N_QUERY, seed=1234))
+    t0 = time.perf_counter()
+    probe()
+    t1 = time.perf_counter() - t0          # first call: includes one-off costs, so this over-estimates (safe)
+    shapes = int(budget_s / max((steps + warmup) * t1, 1e-9))
+    try:
+        import psutil
+        shapes = min(shapes, int(psutil.virtual_memory().available / (6 << 30)))
+    except Exception:
+        shapes = min(shapes, 2)
+    shapes = max(1, min(B_PER_GPU, shapes))
+    step = probe if shapes == 1 else make(synth.forward_batch(shapes, N_SURF, N_QUERY, seed=1234))
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -144,60 +194,50 @@ def cpu_reference_run(steps: int, warmup: int, shapes_per_step: int = 1, max_sec
     for _ in range(steps):
         step()
         done += 1
-        if time.perf_counter() - t0 > max_seconds:
+        if time.perf_counter() - t0 > 2 * budget_s:
             break
     dt = time.perf_counter() - t0
-    qps = done * shapes_per_step * N_QUERY / dt
-    return {"value": qps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} step(s) x {shapes_per_step} shape(s) of {N_SURF} surface pts x {N_QUERY} queries, fwd+bwd+Adam, "
-                      f"torch CPU fp32 ({dt / max(done, 1):.2f} s/step)"}, dt / max(done, 1), done
+    qps = done * shapes * N_QUERY / dt
+    what = ("UNMODIFIED reference model/ (baseline/_ref) via its build_model + train_on_batch_with_cano; FPS = C restatement "
+            "of sampling_gpu.cu (the reference kernel is CUDA-only)") if kind == "reference" else \
+        "oracle port of the reference path (oracle/tdnet_oracle.py)"
+    return {"value": qps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{done} step(s) x {shapes} of the {B_PER_GPU} shape(s) of {N_SURF} surface pts x {N_QUERY} queries, "
+                      f"fwd+bwd+Adam, torch CPU fp32, {dt / max(done, 1):.2f} s/step; {what}"}, dt / max(done, 1), done, shapes
 
 
-def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU, forward_only: bool = False):
-    """NOT the contract's reference arm (that one is the CPU run below): the same restatement of the reference's op chain
-    executed as PyTorch eager ops on cuda:0 (TF32 off; FPS = the reference's own CUDA kernel from oracle/_ref; k-NN = the
-    reference's square_distance + argsort) — the "reference on 1 GPU" number BASELINE.json's >= 10x target is stated
-    against. `--impl reference --ref-device cuda`."""
+def gpu_reference_run(steps: int, warmup: int, shapes_per_step: int = B_PER_GPU, forward_only: bool = False, device=None):
+    """The "reference on 1 GPU" number BASELINE.json's >= 10x target is stated against: the unmodified reference model
+    (baseline/_ref) in PyTorch eager on one B200, TF32 off, FPS = the reference's own CUDA kernel rebuilt for sm_100a
+    (oracle/_ref). Not the contract's reference arm (that one is the CPU run); reported as `gpu_reference` in our line
+    and by `--impl reference --ref-device cuda`."""
     from nsdp_b200 import synth
-    from nsdp_b200.model import build_model
-    from oracle import tdnet_oracle as orc
-
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    dev = torch.device("cuda", 0)
-    cfg = synth.make_config("forward")
-    model, *_ = build_model(cfg)
-    schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
-    sd = {k: v.to(dev) for k, v in synth.named_state_dict(schema, seed=0).items()}
-    params = [v.requires_grad_(True) for k, v in sd.items() if k.rsplit(".", 1)[-1] in ("weight", "bias")]
-    opt = torch.optim.Adam(params, lr=5e-4)
-    batch = {k: v.to(dev) for k, v in synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234).items()}
-
-    def train_step():
-        opt.zero_grad()
-        pred = orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False,
-                                 training=True)
-        loss = orc.l2_loss(pred, batch["space_samples_tgt"])
-        loss.backward()
-        opt.step()
-        return loss.item()
-
-    def eval_forward():
-        with torch.no_grad():
-            return orc.tdnet_forward(sd, "", batch["space_samples_src"], batch["surface_samples_inputs"], cfg["model"], False)
-
-    step = eval_forward if forward_only else train_step
-    for _ in range(max(warmup, 1)):
-        step()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / steps
-    return shapes_per_step * N_QUERY / (ms * 1e-3), ms, torch.cuda.max_memory_allocated() / 2 ** 30
+    dev = device or torch.device("cuda", 0)
+    try:
+        kind, make = _reference_api(dev)
+        batch = {k: v.to(dev) for k, v in synth.forward_batch(shapes_per_step, N_SURF, N_QUERY, seed=1234).items()}
+        step = make(batch, forward_only)
+        torch.cuda.reset_peak_memory_stats(dev)
+        for _ in range(max(warmup, 1)):
+            step()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / steps
+        return {"value": shapes_per_step * N_QUERY / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "warmup": max(warmup, 1), "kind": kind, "peak_memory_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                "what": "unmodified reference model (baseline/_ref) as PyTorch eager on the same GPU, fp32 with TF32 off, "
+                        "FPS = the reference's own CUDA kernel (oracle/_ref), same batch/weights/optimizer"
+                        if kind == "reference" else "oracle port of the reference op chain as PyTorch eager on the same GPU"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
 
 
 def run_reference_arm(args):
@@ -205,19 +245,20 @@ def run_reference_arm(args):
     if rank != 0:
         return
     if args.ref_device == "cuda":
-        qps, ms, gib = gpu_reference_run(args.steps, args.warmup, forward_only=args.forward_only)
-        emit_line({"impl": "reference", "metric": METRIC_FWD if args.forward_only else METRIC, "value": qps, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-                   "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                   "vs_baseline": None, "dtype": "f32 (TF32 off)", "data": "synthetic",
-                   "config": {"workload": WORKLOAD, "peak_memory_gib": gib,
-                              "note": "restatement of the reference op chain as PyTorch eager on cuda:0 with the reference's "
-                                      "own FPS kernel (oracle/_ref); informational, not the contract's CPU reference arm"}})
+        r = gpu_reference_run(args.steps, args.warmup, forward_only=args.forward_only)
+        emit_line({"impl": "reference", "metric": METRIC_FWD if args.forward_only else METRIC, "value": r["value"], "unit": UNIT,
+                   "n_gpus": 1, "steps": args.steps, "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 off)",
+                   "data": "synthetic", "config": {"workload": WORKLOAD, "peak_memory_gib": r["peak_memory_gib"], "note": r["what"]}})
         return
-    base, s_per_step, done = cpu_reference_run(args.steps, min(args.warmup, 1))
+    base, s_per_step, done, shapes = cpu_reference_run(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+            "steps": done, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (oracle port), bounded sample"},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "surface_pts": N_SURF, "queries": N_QUERY,
+                       "sample_shapes_per_step": shapes,
+                       "note": "reference on the host CPU cores of rank 0's box; value is per-process throughput "
+                               "(query-points/s), cost is linear in shapes"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_line(line)
@@ -395,6 +436,7 @@ def run_ours(args):
 
     roof = None
     cpu = None
+    gpu_ref = None
     # every rank runs the instrumented steps (they contain the gradient all-reduce); rank 0 reports its own numbers
     summary, prof_step_ms, prof_steps = profile_kernels(step_resident)
     if rank == 0:
@@ -436,7 +478,14 @@ def run_ours(args):
             except Exception as exc:   # informational only: never lose the bench line over it
                 print(f"[bench] decoder MLP microbenchmark skipped: {exc}", file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline and not c3:
-            cpu, _, _ = cpu_reference_run(steps=2, warmup=1, max_seconds=60.0)
+            cpu, _, _, _ = cpu_reference_run(steps=2, warmup=1, budget_s=25.0)
+        if world == 1 and not args.no_gpu_reference and not c3:
+            # the >= 10x target's denominator (BASELINE.json north_star): the reference itself on this GPU
+            try:
+                gpu_ref = gpu_reference_run(steps=10, warmup=3, device=dev)
+                gpu_ref["ours_over_reference"] = (B_PER_GPU * N_QUERY * args.steps / (ms_total * 1e-3)) / gpu_ref["value"]
+            except Exception as exc:
+                print(f"[bench] same-GPU reference run skipped: {exc}", file=sys.stderr)
     if world > 1:
         td.barrier()
     if rank == 0:
@@ -456,18 +505,23 @@ def run_ours(args):
                 "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
+            roof["gpu_reference"] = {k: gpu_ref[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "kind", "ours_over_reference")}
         emit_line(line)
     if world > 1:
         td.destroy_process_group()
 
 
 def main():
+    global N_QUERY, N_SURF, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 (default, the headline): forward-deformation TDNet, 8 shapes/GPU; c3 (informational): FlowArbitrary, "
                          "4 shapes/GPU")
@@ -475,7 +529,12 @@ def main():
                     help="informational: eval-mode forward instead of the training step (ours, or --ref-device cuda)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="with --impl reference: cuda = the reference op chain as PyTorch eager on one GPU (informational)")
+    ap.add_argument("--queries", type=int, default=N_QUERY, help=argparse.SUPPRESS)     # contract tests only: shrink the
+    ap.add_argument("--surface", type=int, default=N_SURF, help=argparse.SUPPRESS)      # workload (the line then says so)
     args = ap.parse_args()
+    if (args.queries, args.surface) != (N_QUERY, N_SURF):
+        N_QUERY, N_SURF = args.queries, args.surface
+        WORKLOAD = f"NOT configs[1] (shrunk for a contract test): {N_SURF} surface pts x {N_QUERY} queries"
     import contextlib
     # the API mirrors the reference's progress prints (optimizer specs, parameter counts): keep stdout for the JSON line
     with contextlib.redirect_stdout(sys.stderr):
