@@ -60,7 +60,10 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
     id[i] = 0x7fffffff;
   }
   // +inf distances must still be selectable when N is tiny: FLT_MAX sentinels lose against any finite d,
-  // and genuine inf/NaN distances are never inserted (same as "sorted last").
+  // and genuine inf/NaN distances are never inserted (same as "sorted last"). A query or cloud with non-finite
+  // coordinates (a diverging canonicaliser in FlowArbitrary feeds network OUTPUTS into this search) therefore leaves
+  // slots unfilled: they are reported as index min(slot, N-1) with a NaN distance, so downstream gathers stay in bounds
+  // and the NaNs propagate numerically, as they would through the reference's argsort.
   const int j0 = s * split_len;
   const int j1 = min(N, j0 + split_len);
   for (int base = j0; base < j1; base += kKnnChunk) {
@@ -84,12 +87,12 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
     int32_t *oi = out_idx + ((size_t)b * M + qi) * k;
 #pragma unroll
     for (int i = 0; i < KMAX; ++i)
-      if (i < k) oi[i] = id[i];
+      if (i < k) oi[i] = id[i] < N ? id[i] : min(i, N - 1);   // unfilled slot (non-finite distances): a VALID index, see below
     if (out_d2) {
       float *od = out_d2 + ((size_t)b * M + qi) * k;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i)
-        if (i < k) od[i] = dist[i];
+        if (i < k) od[i] = id[i] < N ? dist[i] : __int_as_float(0x7fc00000);
     }
   } else {
     const size_t off = (((size_t)b * M + qi) * S + s) * k;
@@ -104,7 +107,7 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
 
 // S-way merge of sorted partial lists; one thread per query.
 __global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, long long BM,
-                                 int k, int S, int32_t *__restrict__ out_idx, float *__restrict__ out_d2) {
+                                 int k, int S, int N, int32_t *__restrict__ out_idx, float *__restrict__ out_d2) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= BM) return;
   const float *pd = part_d + (size_t)q * S * k;
@@ -123,8 +126,8 @@ __global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t
       }
     }
     head[bs]++;
-    out_idx[(size_t)q * k + t] = bi;
-    if (out_d2) out_d2[(size_t)q * k + t] = bd;
+    out_idx[(size_t)q * k + t] = bi < N ? bi : min(t, N - 1);
+    if (out_d2) out_d2[(size_t)q * k + t] = bi < N ? bd : __int_as_float(0x7fc00000);
   }
 }
 
@@ -177,7 +180,7 @@ extern "C" int nsdp_knn_f32(const float *query, const float *ref, int B, int M, 
   if (rc != NSDP_OK) return rc;
   if (S > 1) {
     const long long BM = (long long)B * M;
-    knn_merge_kernel<<<(unsigned)ceil_div(BM, 128ll), 128, 0, st>>>(part_d, part_i, BM, k, S, out_idx, out_d2);
+    knn_merge_kernel<<<(unsigned)ceil_div(BM, 128ll), 128, 0, st>>>(part_d, part_i, BM, k, S, N, out_idx, out_d2);
     rc = check_launch();
   }
   return rc;

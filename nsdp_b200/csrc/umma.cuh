@@ -48,8 +48,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike). mbarrier.try_wait may itself block
-// for a hardware-defined interval, so the bound is on TIME (%globaltimer): 2 s for the first wait that fails,
-// 20 us for every wait once the error flag is up. A timed-out kernel produces garbage that the parity tests catch.
+// for a hardware-defined interval, so the bound is on TIME (%globaltimer): 2 s. A wait that times out must not be
+// walked past (the operands / TMEM accumulators behind it are not ready): the error word is set for post-mortems and
+// the kernel TRAPS, so the launch fails with a sticky CUDA error that the next check() / synchronize raises on the
+// host instead of silently corrupting outputs and gradients.
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -65,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
       const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
       if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
         if (err) atomicExch(err, 1);
-        break;
+        __trap();
       }
     }
   }
@@ -98,7 +100,7 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity, i
       const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
       if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
         if (err) atomicExch(err, 1);
-        break;
+        __trap();
       }
     }
   }

@@ -19,7 +19,6 @@ from typing import Iterable, List, Optional
 import torch
 import torch.distributed as td
 
-_FLAT = {}  # id(model) -> (flat buffer, [params])
 
 
 def is_active() -> bool:
@@ -54,43 +53,175 @@ def broadcast_parameters(model, src: int = 0) -> None:
         td.broadcast(t.data, src=src)
 
 
-def _flat_for(model) -> tuple:
-    key = id(model)
-    params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
-    entry = _FLAT.get(key)
-    n = sum(p.numel() for p in params)
-    if entry is None or entry[0].numel() != n or entry[0].device != params[0].device:
-        flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
-        _FLAT[key] = entry = (flat, params)
-    return entry
+class _GradBuckets:
+    """All gradients of a model as views of ONE flat fp32 buffer, laid out in REVERSE parameter order (roughly the order
+    in which backward() finalises them: decoder first, early encoder layers last) and cut into contiguous buckets of
+    >= `bucket_bytes`. A post-accumulate hook per parameter counts a bucket down; as soon as a bucket (and every bucket
+    before it: all ranks must issue collectives in the same order) is complete its slice is all-reduced asynchronously
+    — NCCL runs it on its own stream, overlapped with the rest of the backward — and `finish()` only waits.
+
+    No per-parameter copies into or out of the flat buffer, no `div_` (ReduceOp.AVG on NCCL; one scale per bucket on
+    gloo). Parameters that never receive a gradient (the unused q/k/v weights of the pos_only block) keep zeros in their
+    views; which ones do is learnt on the first step, during which every bucket is reduced at the end."""
+
+    def __init__(self, model, bucket_bytes: int = 4 << 20):
+        self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad][::-1]
+        p0 = self.params[0]
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=p0.dtype, device=p0.device)
+        self.views, self.bucket_of, self.bounds = [], [], [0]
+        off, cur = 0, 0
+        for p in self.params:
+            n = p.numel()
+            self.views.append(self.flat[off:off + n].view_as(p))
+            self.bucket_of.append(len(self.bounds) - 1)
+            off += n
+            cur += n * p.element_size()
+            if cur >= bucket_bytes:
+                self.bounds.append(off)
+                cur = 0
+        if self.bounds[-1] != off:
+            self.bounds.append(off)
+        self.nb = len(self.bounds) - 1
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.expected = None                       # per bucket: the parameters whose hooks fire (learnt on step 1)
+        self.remaining = None
+        self.fired_ids = set()
+        self.launched = 0                          # buckets [0, launched) are in flight / done this step
+        self.works, self.late = [], []
+        self.synced_state = False
+        self.avg = td.get_backend() == "nccl"
+        self.overlap = os.environ.get("NSDP_B200_OVERLAP", "1") != "0"
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def attach(self) -> None:
+        for p, v in zip(self.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def zero(self) -> None:
+        self.attach()
+        self.flat.zero_()
+        self.fired_ids = set()
+        self.remaining = [set(s) for s in self.expected] if (self.expected is not None and self.overlap) else None
+        self.launched = 0
+        self.works, self.late = [], []
+
+    def _launch(self, b: int) -> None:
+        t = self.flat[self.bounds[b]:self.bounds[b + 1]]
+        if self.avg:
+            self.works.append((td.all_reduce(t, op=td.ReduceOp.AVG, async_op=True), None))
+        else:
+            self.works.append((td.all_reduce(t, op=td.ReduceOp.SUM, async_op=True), t))
+
+    def _hook(self, p) -> None:
+        i = self.index.get(id(p))
+        if i is None or not is_active():
+            return
+        if p.grad.data_ptr() != self.views[i].data_ptr():
+            self.views[i].copy_(p.grad)            # somebody replaced .grad (zero_grad(set_to_none=True)): fold it back
+            p.grad = self.views[i]
+        b = self.bucket_of[i]
+        self.fired_ids.add(i)
+        if b < self.launched:                      # arrived while / after its bucket was being reduced
+            self.late.append(i)
+            return
+        if self.remaining is None:
+            return
+        self.remaining[b].discard(i)
+        while self.launched < self.nb and not self.remaining[self.launched]:
+            self._launch(self.launched)
+            self.launched += 1
+
+    def finish(self) -> None:
+        while self.launched < self.nb:
+            self._launch(self.launched)
+            self.launched += 1
+        world = td.get_world_size()
+        for w, t in self.works:
+            w.wait()
+            if t is not None:
+                t.mul_(1.0 / world)
+        late = self.late
+        self.expected = [set(i for i in self.fired_ids if self.bucket_of[i] == b) for b in range(self.nb)] \
+            if (self.expected is None or late) else self.expected
+        self.works, self.late = [], []
+        if late:
+            # its in-place accumulation raced with the collective in flight: this step's gradient of that bucket is not
+            # trustworthy. Only possible when a parameter that had no gradient on the first step gets one later.
+            raise RuntimeError("gradients of parameters %s arrived after their bucket had been all-reduced (the set of "
+                               "parameters with gradients changed between steps); set NSDP_B200_OVERLAP=0" % sorted(set(late)))
+
+
+_BUCKETS = {}  # id(model) -> _GradBuckets
+
+
+def _buckets_for(model) -> _GradBuckets:
+    bk = _BUCKETS.get(id(model))
+    if bk is None:
+        bk = _BUCKETS[id(model)] = _GradBuckets(model, int(os.environ.get("NSDP_B200_BUCKET_BYTES", 4 << 20)))
+    return bk
+
+
+@torch.no_grad()
+def sync_training_state(model, optimizer=None) -> None:
+    """Rank 0's parameters, buffers and optimizer state become everybody's. build_model() broadcasts the initial weights,
+    but an unchanged train.py loads checkpoints AFTER build_model (train.py:152-156): called on the first train step so
+    that replicas that resumed from different files (or did not resume) cannot drift apart silently."""
+    if not is_active():
+        return
+    broadcast_parameters(model)
+    if optimizer is None:
+        return
+    dev = next(model.parameters()).device
+    # the replicas must agree on the STRUCTURE of the optimizer state before tensors can be broadcast
+    n_state = torch.tensor([sum(len(s) for s in optimizer.state.values())], dtype=torch.int64, device=dev)
+    lo, hi = n_state.clone(), n_state.clone()
+    td.all_reduce(lo, op=td.ReduceOp.MIN)
+    td.all_reduce(hi, op=td.ReduceOp.MAX)
+    if int(lo) != int(hi):
+        raise RuntimeError("data-parallel replicas resumed from different checkpoints (optimizer state present on some "
+                           "ranks only): every rank must read rank 0's model_*/opt_* files (nsdp_b200.launch does this)")
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            for k, v in sorted(optimizer.state.get(p, {}).items()):
+                if torch.is_tensor(v):
+                    t = v.to(dev) if v.device != dev else v
+                    td.broadcast(t, src=0)
+                    if t is not v:
+                        v.copy_(t)
+
+
+def zero_grad(model, optimizer) -> None:
+    """optimizer.zero_grad() of the reference's train_on_batch_* (deformation_networks.py:65). Under data parallelism the
+    gradients live in one flat buffer (one memset) and keep their storage from step to step."""
+    if not is_active():
+        optimizer.zero_grad()
+        return
+    bk = _buckets_for(model)
+    if not bk.synced_state:
+        sync_training_state(model, optimizer)
+        bk.synced_state = True
+    bk.zero()
 
 
 @torch.no_grad()
 def allreduce_gradients(model) -> None:
-    """Average gradients across ranks with a single collective over one flat fp32 buffer (17.97 MB for a
-    TDNet, 35.94 MB for FlowArbitrary). Parameters that received no gradient (the unused q/k/v weights of the
-    pos_only block) contribute zeros, so every rank reduces the same layout."""
+    """Average the gradients across ranks (17.97 MB for a TDNet, 35.94 MB for FlowArbitrary). When the step went through
+    zero_grad() above, most of the traffic already left during backward(); this waits for it and reduces what is left.
+    Parameters that received no gradient contribute zeros, so every rank reduces the same layout. A model whose
+    gradients were produced without zero_grad() (plain `.backward()` on fresh `.grad`s) is folded into the flat buffer
+    first."""
     if not is_active():
         return
-    flat, params = _flat_for(model)
-    off = 0
-    for p in params:
-        n = p.numel()
+    bk = _buckets_for(model)
+    for p, v in zip(bk.params, bk.views):
         if p.grad is None:
-            flat[off:off + n].zero_()
-        else:
-            flat[off:off + n].copy_(p.grad.reshape(-1))
-        off += n
-    td.all_reduce(flat, op=td.ReduceOp.SUM)
-    flat.div_(td.get_world_size())
-    off = 0
-    for p in params:
-        n = p.numel()
-        if p.grad is None:
-            p.grad = flat[off:off + n].reshape(p.shape).clone()
-        else:
-            p.grad.copy_(flat[off:off + n].reshape(p.shape))
-        off += n
+            p.grad = v
+        elif p.grad.data_ptr() != v.data_ptr():
+            v.copy_(p.grad)
+            p.grad = v
+    bk.finish()
 
 
 def shard_batch(data_dict: dict, rank: Optional[int] = None, world: Optional[int] = None) -> dict:

@@ -38,6 +38,23 @@ def install_aliases() -> None:
     sys.modules["pointnet2_ops_lib.pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
 
 
+def mirror_checkpoints(shared_dir: str, private_dir: str) -> None:
+    """Resume must give every replica the SAME weights, optimizer state and epoch (utils/checkpoints.py:8-31 picks the
+    newest model_%05d/opt_%05d and modelbest_* of the directory it is pointed at): a rank's private directory only
+    receives its WRITES; what it READS at start-up are links to rank 0's checkpoint files, replacing whatever an earlier
+    run with another world size left there. Rank 0 writes nothing before the first epoch ends, so all ranks list the
+    same files. (nsdp_b200.dist.sync_training_state additionally re-broadcasts rank 0's state on the first step.)"""
+    os.makedirs(private_dir, exist_ok=True)
+    is_ckpt = lambda f: f.startswith(("model_", "opt_", "modelbest_"))   # noqa: E731
+    for f in os.listdir(private_dir):
+        if is_ckpt(f):
+            os.remove(os.path.join(private_dir, f))
+    if os.path.isdir(shared_dir):
+        for f in os.listdir(shared_dir):
+            if is_ckpt(f):
+                os.symlink(os.path.abspath(os.path.join(shared_dir, f)), os.path.join(private_dir, f))
+
+
 def rewrite_argv_for_rank(argv, rank: int, world: int, scratch_dir: str):
     """argv = [train.py, config.yaml, ...] -> the same with `--seed base+rank` and, for rank > 0, a copy of the config whose
     `experiment.out_dir` is `<out_dir>/rank<r>`. Other scripts and single-process runs are returned unchanged."""
@@ -63,7 +80,9 @@ def rewrite_argv_for_rank(argv, rank: int, world: int, scratch_dir: str):
             ci = pos[0]
             with open(argv[ci]) as f:
                 cfg = yaml.safe_load(f)
+            shared = os.path.join(str(cfg["experiment"]["out_dir"]), str(cfg["experiment"].get("name", "")))
             cfg["experiment"]["out_dir"] = os.path.join(str(cfg["experiment"]["out_dir"]), f"rank{rank}")
+            mirror_checkpoints(shared, os.path.join(cfg["experiment"]["out_dir"], str(cfg["experiment"].get("name", ""))))
             os.makedirs(scratch_dir, exist_ok=True)
             out = os.path.join(scratch_dir, f"rank{rank}_" + os.path.basename(argv[ci]))
             with open(out, "w") as f:

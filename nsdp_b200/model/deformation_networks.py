@@ -45,7 +45,7 @@ class Deformation_Networks(nn.Module):
 
 
 def train_on_batch_with_cano(model, optimizer, data_dict, config):
-    optimizer.zero_grad()
+    nsdp_dist.zero_grad(model, optimizer)
     pred = model(data_dict["space_samples_src"], data_dict["surface_samples_inputs"])
     loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
     loss.backward()

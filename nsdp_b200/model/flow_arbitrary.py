@@ -2,6 +2,9 @@
 backward TDNet (for the space samples AND the surface samples), then canonical -> target with the forward
 TDNet whose encoder input is cat[surface_src2cano, surface_tgt, mask].
 
+Inference (test_on_batch_with_arbitrary) encodes each distinct encoder input once: 2 encoder passes where the reference
+runs 6 (flow_arbitrary.py:65-85).
+
 The reference runs the canonicalise ENCODER twice on identical input (flow_arbitrary.py:19-20). Here it is
 encoded once and decoded for both query sets; to stay bit-compatible with the reference's BatchNorm
 bookkeeping in train() mode (every BN updates its running stats twice per step) the single
@@ -61,7 +64,7 @@ def _split_inputs(data_dict):
 
 
 def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
-    optimizer.zero_grad()
+    nsdp_dist.zero_grad(model, optimizer)
     src, tgt, mask = _split_inputs(data_dict)
     pred = model(data_dict["space_samples_src"], src, tgt, mask)
     loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
@@ -81,8 +84,21 @@ def validate_on_batch_with_arbitrary(model, data_dict, config):
 @torch.no_grad()
 def test_on_batch_with_arbitrary(model, data_dict, config, compute_loss=False):
     src, tgt, mask = _split_inputs(data_dict)
-    data_dict["surface_samples_tgt_pred"] = model(src, src, tgt, mask)
-    verts_pred = model(data_dict["verts_src"], src, tgt, mask)
+    if model.training:
+        # train-mode BatchNorm: every encoder pass updates running stats, keep the reference's passes
+        data_dict["surface_samples_tgt_pred"] = model(src, src, tgt, mask)
+        verts_pred = model(data_dict["verts_src"], src, tgt, mask)
+    else:
+        # The reference's two model(...) calls (flow_arbitrary.py:71-79) encode the same source surface with the
+        # canonicaliser 2 x 2 times and the same cat[surface_src2cano, tgt, mask] with the deform net twice: in eval mode
+        # all of that is identical work. Encode each once (2 encoder passes instead of 6), then decode per query set; the
+        # surface samples' canonical positions double as the first query set's.
+        cano, deform = model.model_canonicalize, model.model_deform
+        cano_enc = cano.encode(src)
+        surface_src2cano = cano.decode(src.contiguous(), cano_enc)
+        deform_enc = deform.encode(torch.cat([surface_src2cano, tgt, mask], dim=-1).contiguous())
+        data_dict["surface_samples_tgt_pred"] = deform.decode(surface_src2cano, deform_enc)
+        verts_pred = deform.decode(cano.decode(data_dict["verts_src"], cano_enc), deform_enc)
     data_dict["verts_tgt_pred"] = verts_pred
     if compute_loss:
         loss = compute_l2_error(verts_pred, data_dict["verts_tgt"])

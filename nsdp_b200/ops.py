@@ -263,7 +263,7 @@ class _VectorAttention(torch.autograd.Function):
     inputs + the (B,M,D) result and softmax statistics — no [pairs, D] activation is saved."""
 
     @staticmethod
-    def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign):
+    def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, grad_enabled=True):
         tensors = dict(xyz_c=xyz_c, xyz_n=xyz_n, qp=qp, kp=kp, vp=vp, gq=gq, gv=gv, wd0=wd0, bd0=bd0, wd2t=wd2t,
                        wpt=wpt, wg2t=wg2t, pc=pc, vc=vc)
         for n, t in tensors.items():
@@ -273,7 +273,10 @@ class _VectorAttention(torch.autograd.Function):
             _chk_i32("idx", idx)
         a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign)
         out = torch.empty((a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device)
-        need_bwd = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad() (parameters keep requires_grad=True) and Function.forward always runs
+        # with grad mode off, so the caller's grad mode comes in as an argument: eval / validate / test.py forwards
+        # must not allocate and write the (2,B,M,D) softmax statistics (640 MB per decoder call at the bench size)
+        need_bwd = bool(grad_enabled) and any(ctx.needs_input_grad)
         stats = torch.empty((2, a.B, a.M, a.D), dtype=torch.float32, device=xyz_c.device) if need_bwd else None
         L = _lib.lib()
         saved = None
@@ -308,9 +311,14 @@ class _VectorAttention(torch.autograd.Function):
         def z(t, flag):
             return torch.zeros_like(t) if (t is not None and flag) else None
 
+        # the tensor-core kernels always reduce the three d x d weight gradients (NSDP_ERR_INVALID_ARGUMENT on NULL): a
+        # frozen network (requires_grad_(False), test-time optimisation of queries / latents) gets scratch buffers that
+        # are dropped below
+        wneed = (lambda i: True) if a.impl != 1 else (lambda i: need[i])
+
         g = dict(d_xyz_c=z(xyz_c, need[0]), d_xyz_n=z(xyz_n, need[1]), d_qp=z(qp, need[3]), d_kp=z(kp, need[4]),
                  d_vp=z(vp, need[5]), d_gq=z(gq, need[6]), d_gv=z(gv, need[7]), d_wd0=z(wd0, need[8]),
-                 d_bd0=z(bd0, need[9]), d_wd2t=z(wd2t, need[10]), d_wpt=z(wpt, need[11]), d_wg2t=z(wg2t, need[12]),
+                 d_bd0=z(bd0, need[9]), d_wd2t=z(wd2t, wneed(10)), d_wpt=z(wpt, wneed(11)), d_wg2t=z(wg2t, wneed(12)),
                  d_pc=z(pc, need[13]), d_vc=z(vc, need[14]))
         # xyz_c and xyz_n may be the SAME tensor (self attention): both gradients are returned and autograd
         # sums them.
@@ -326,12 +334,14 @@ class _VectorAttention(torch.autograd.Function):
                                            _p(ws), ws_bytes, _stream()), "nsdp_vattn_bwd_f32")
         _count()
         return (g["d_xyz_c"], g["d_xyz_n"], None, g["d_qp"], g["d_kp"], g["d_vp"], g["d_gq"], g["d_gv"], g["d_wd0"],
-                g["d_bd0"], g["d_wd2t"], g["d_wpt"], g["d_wg2t"], g["d_pc"], g["d_vc"], None)
+                g["d_bd0"], g["d_wd2t"] if need[10] else None, g["d_wpt"] if need[11] else None,
+                g["d_wg2t"] if need[12] else None, g["d_pc"], g["d_vc"], None, None)
 
 
 def vector_attention(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign=1.0, gq=None, gv=None):
     """Fused pair-level vector attention (see nsdp_vattn_args in include/nsdp_b200.h)."""
-    return _VectorAttention.apply(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, float(sign))
+    return _VectorAttention.apply(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, float(sign),
+                                  torch.is_grad_enabled())
 
 
 def _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo) -> TailArgs:

@@ -289,7 +289,18 @@ def encoder(sd, p, x, cfg, has_features, training=False, trace: Optional[dict] =
 # --------------------------------------------------------------------------------------
 # decoder
 # --------------------------------------------------------------------------------------
-def cross_transformer_block(sd, p, xyz_q, z, anchors, anchor_feats, nneigh):
+def _note_kink(kink, pre, rows_dim0=2):
+    """Test aid: per query, the smallest |ReLU pre-activation| seen so far, relative to that layer's rms (a gradient is
+    discontinuous where a pre-activation crosses 0, so parity tests exclude queries sitting on a kink on BOTH sides)."""
+    if kink is None:
+        return
+    with torch.no_grad():
+        m = pre.detach().abs() / pre.detach().pow(2).mean().sqrt().clamp_min(1e-30)
+        m = m.reshape(m.shape[0], m.shape[1], -1).min(dim=-1)[0]
+        kink["margin"] = m if "margin" not in kink else torch.minimum(kink["margin"], m)
+
+
+def cross_transformer_block(sd, p, xyz_q, z, anchors, anchor_feats, nneigh, kink=None):
     """CrossTransformerBlock.forward, model/decoder/blocks.py:48-95 (2-D lat_rep branch,
     reduce_dim=True, separate_delta=True — numerically the same delta used twice)."""
     with torch.no_grad():
@@ -302,21 +313,26 @@ def cross_transformer_block(sd, p, xyz_q, z, anchors, anchor_feats, nneigh):
     vv = torch.cat([index_points(_lin(sd, p + ".w_vs", anchor_feats, bias=False), idx), vg], dim=2)
     rel = xyz_q[:, :, None] - index_points(anchors, idx)
     pos = _mlp2(sd, p + ".fc_delta", rel)
+    _note_kink(kink, _lin(sd, p + ".fc_delta.0", rel))
     pos = torch.cat([pos, torch.zeros(B, Q, 1, pos.shape[-1], dtype=pos.dtype, device=pos.device)], dim=2)
+    _note_kink(kink, _lin(sd, p + ".fc_gamma.0", q - kk + pos))
     attn = F.softmax(_mlp2(sd, p + ".fc_gamma", q - kk + pos), dim=-2)
     return (attn * (vv + pos)).sum(dim=2)
 
 
-def decoder(sd, p, xyz_q, enc, cfg):
+def decoder(sd, p, xyz_q, enc, cfg, kink=None):
     """CrossTransformerDecoder.forward, model/decoder/crosstransformer_decoder.py:45-70 with
     ResnetBlockFC (model/decoder/blocks.py:133-142). cfg = the YAML ``decoder_kwargs``."""
     lat = cross_transformer_block(sd, p + ".ct1", xyz_q, enc["z"], enc["anchors"], enc["anchor_feats"],
-                                  cfg.get("nneigh", 7))
+                                  cfg.get("nneigh", 7), kink=kink)
     net = _lin(sd, p + ".init_enc", lat)
     for i in range(cfg.get("n_blocks", 5)):
         net = net + _lin(sd, f"{p}.fc_c.{i}", lat)
+        _note_kink(kink, net)
         h = _lin(sd, f"{p}.blocks.{i}.fc_0", F.relu(net))
+        _note_kink(kink, h)
         net = net + _lin(sd, f"{p}.blocks.{i}.fc_1", F.relu(h))
+    _note_kink(kink, net)
     return _lin(sd, p + ".fc_out", F.relu(net))
 
 
@@ -324,7 +340,7 @@ def decoder(sd, p, xyz_q, enc, cfg):
 # whole networks
 # --------------------------------------------------------------------------------------
 def tdnet_forward(sd: Dict[str, torch.Tensor], prefix: str, points, surface, model_cfg, no_input_corr,
-                  training=False, trace=None):
+                  training=False, trace=None, kink=None):
     """Deformation_Networks.forward, model/deformation_networks.py:43-60. `prefix` is '' for a bare
     TDNet or 'model_deform.' / 'model_canonicalize.' inside FlowArbitrary."""
     if no_input_corr:
@@ -335,7 +351,7 @@ def tdnet_forward(sd: Dict[str, torch.Tensor], prefix: str, points, surface, mod
                       training=training, trace=trace)
     if trace is not None:
         trace.update({"z": enc["z"], "anchors": enc["anchors"], "anchor_feats": enc["anchor_feats"]})
-    return decoder(sd, prefix + "decoder", points, enc, model_cfg["decoder_kwargs"])
+    return decoder(sd, prefix + "decoder", points, enc, model_cfg["decoder_kwargs"], kink=kink)
 
 
 def flow_arbitrary_forward(sd, space_src, surf_src, surf_tgt, mask, model_cfg, training=False):

@@ -34,3 +34,10 @@ def _built_library():
     build()
     from oracle.build import build as build_oracle
     build_oracle()
+
+
+@pytest.fixture(scope="session")
+def golden_r2():
+    """Round-2 fixtures from the live reference (tests/golden/make_golden_r2.py): per-block encoder activations and the
+    staged FlowArbitrary training step."""
+    return np.load(os.path.join(GOLDEN_DIR, "tdnet_reference_r2.npz"))

@@ -1,0 +1,234 @@
+"""Round-2 golden fixtures, minted by running the LIVE reference (/root/reference/model, unmodified) on the CPU:
+
+    python tests/golden/make_golden_r2.py        ->  tests/golden/tdnet_reference_r2.npz
+
+1. `trace_eval::<module>` / `trace_train::<module>`: the output of every encoder block (transformer_begin, each
+   TransitionDown, ElementwiseMLP, TransformerBlock, final block) captured with forward hooks on the reference modules
+   (model/encoder/pointransformer.py:100-140) — eval mode on the C1 cloud, train mode (batch-statistics BatchNorm) on the
+   training batch of make_golden.py. Tensors with more than 200 rows per shape keep every 8th row, the others every 2nd (consumers apply `thin` too).
+2. Forward-net training step in fp64 (the reference with .double(): the TRUTH SURVEY 8d's "< 1e-3 vs fp64" bar refers to),
+   with queries that sit on a ReLU kink masked out of the loss (`fw64_keep`): prediction, d/d query, d/d surface, and
+   EVERY parameter gradient — a few tensors in full, all of them as norm + 4 seeded random projections <g, r_k>
+   (r_k ~ N(0,1), `projection_vectors`), so that consumers hold every tensor to a relative-L2 bar without an 18 MB fixture.
+3. FlowArbitrary training step, STAGED (model/flow_arbitrary.py:15-27): (a) stage-1 outputs of the fp32 reference in train
+   mode; (b) stage 2 in fp64 teacher-forced with (a) -> loss, gradients reaching the stage-1 outputs, deform-net parameter
+   gradients; (c) stage-1 backward in fp64 driven by (b)'s gradients -> canonicalise-net parameter gradients. Stage 2's
+   FPS / k-NN are discontinuous in stage-1 outputs, hence the teacher forcing (tests/test_gpu_tdnet.py).
+Same shim as make_golden.py for the CUDA-only FPS kernel.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from nsdp_b200 import synth  # noqa: E402
+from make_golden import import_reference, schema_of  # noqa: E402
+from oracle import tdnet_oracle as orc  # noqa: E402
+
+KINK = 1e-4   # relative pre-activation margin below which a query is left out of gradient comparisons (see main, part 2)
+
+NPROJ = 4
+TRACED = ("transformer_begin", "transition_downs.", "elementwise_extras.", "transformer_downs.", "elementwise.",
+          "final_transformers.", "final_elementwise.")
+FULL_GRADS = ("decoder.fc_out.weight", "decoder.ct1.fc_gamma.0.weight", "decoder.ct1.fc_delta.0.weight", "decoder.ct1.w_ks.weight",
+              "encoder.transformer_begin.fc_delta.2.weight", "encoder.elementwise.1.conv1.weight", "encoder.fc_middle.0.weight",
+              "model_deform.decoder.fc_out.weight", "model_deform.decoder.ct1.fc_gamma.0.weight",
+              "model_deform.encoder.transformer_begin.fc_delta.0.weight", "model_deform.encoder.transformer_downs.0.fc_gamma.2.weight",
+              "model_canonicalize.decoder.fc_out.weight", "model_canonicalize.decoder.blocks.4.fc_1.weight",
+              "model_canonicalize.encoder.transformer_begin.fc_gamma.0.weight", "model_canonicalize.encoder.enc_sdf.weight"
+              if False else "model_canonicalize.encoder.transformer_downs.0.fc_delta.2.weight")
+
+
+def projection_vectors(name: str, numel: int) -> np.ndarray:
+    """(NPROJ, numel) float64 N(0,1), a pure function of the parameter name."""
+    rng = np.random.default_rng(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    return rng.standard_normal((NPROJ, numel))
+
+
+def thin(t: torch.Tensor) -> np.ndarray:
+    a = t.detach().numpy()
+    return a[:, ::8] if (a.ndim == 3 and a.shape[1] > 200) else (a[:, ::2] if a.ndim == 3 else a)
+
+
+def trace_encoder(encoder, fn):
+    out, hooks = {}, []
+    for name, mod in encoder.named_modules():
+        if name and any(name == t or (name.startswith(t) and name[len(t):].isdigit()) for t in TRACED):
+            def hook(_m, _i, o, name=name):
+                out[name] = thin(o[1] if isinstance(o, tuple) else o)
+            hooks.append(mod.register_forward_hook(hook))
+    fn()
+    for h in hooks:
+        h.remove()
+    return out
+
+
+def main():
+    torch.set_num_threads(8)
+    ref = import_reference()
+    gold = {}
+
+    def build(mtype):
+        cfg = synth.make_config(mtype)
+        m, *_ = ref.build_model(cfg)
+        m.load_state_dict(synth.named_state_dict([(k, s) for k, s in schema_of(m)], seed=0))
+        return m
+
+    # ---- 1. per-block activation traces -------------------------------------------------------------------------------
+    m = build("forward").eval()
+    b = synth.forward_batch(1, 1024, 2048, seed=1234, fp16_grid=False)
+    with torch.no_grad():
+        tr = trace_encoder(m.encoder, lambda: m.encoder(b["surface_samples_inputs"]))
+    for k, v in tr.items():
+        gold["trace_eval::" + k] = v
+    m = build("forward").train()
+    b3 = synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
+    with torch.no_grad():
+        tr = trace_encoder(m.encoder, lambda: m.encoder(b3["surface_samples_inputs"]))
+    for k, v in tr.items():
+        gold["trace_train::" + k] = v
+
+    # ---- 2. forward-net training step against fp64 TRUTH, kink rows masked out of the loss -----------------------------
+    # Gradients are discontinuous where a ReLU pre-activation crosses 0: a 1e-7 perturbation flips the mask of a query that
+    # sits on a kink and moves d/d(query) by O(1) for that row (measured here: fp32 reference vs fp64 reference differ by
+    # 5e-4 .. 2e-3 on d/d query, and by 1e-6 once the 5 % of queries with a relative margin < 1e-5 are left out). The
+    # protocol therefore (a) takes the fp64 run of the reference as the truth, (b) removes from the LOSS every query
+    # whose smallest decoder pre-activation (relative to the layer's rms; oracle in fp64, which equals the reference to
+    # 1e-15) is below KINK, on both sides.
+    def keep_mask(prefix, sd64, points, surface, no_input_corr):
+        kink = {}
+        with torch.no_grad():
+            orc.tdnet_forward(sd64, prefix, points.double(), surface.double(), mcfg, no_input_corr, training=False, kink=kink)
+        return (kink["margin"] > KINK)
+
+    def dump_grads(tag, module, prefix="", twin32=None):
+        """`twin32`: the same module of the fp32 reference after the same (masked, teacher-forced) backward: its relative
+        L2 distance from the fp64 truth is stored per tensor — the reference's OWN fp32 noise (ReLU flips inside the
+        encoder cannot be masked out), which consumers use as the yardstick: bar = max(1e-3, 3 x that)."""
+        names, norms, projs, ref32 = [], [], [], []
+        t32 = dict(twin32.named_parameters()) if twin32 is not None else {}
+        for k, p in module.named_parameters():
+            g32 = t32.get(k)
+            k = prefix + k
+            g = np.zeros(p.numel()) if p.grad is None else p.grad.numpy().astype(np.float64).ravel()
+            names.append(k)
+            norms.append(-1.0 if p.grad is None else float(np.linalg.norm(g)))
+            projs.append(projection_vectors(k, g.size) @ g)
+            ref32.append(0.0 if (g32 is None or g32.grad is None or norms[-1] <= 0) else
+                         float(np.linalg.norm(g32.grad.numpy().astype(np.float64).ravel() - g) / norms[-1]))
+            if k in FULL_GRADS:
+                gold[f"{tag}_grad::{k}"] = p.grad.numpy().astype(np.float32)
+        gold[f"{tag}_names"] = np.array(names)
+        gold[f"{tag}_gradnorms"] = np.array(norms, np.float64)
+        gold[f"{tag}_gradproj"] = np.array(projs, np.float64)
+        gold[f"{tag}_ref32err"] = np.array(ref32, np.float64)
+
+    def masked_l2(pred, gt, keep):
+        return torch.mean(keep.to(pred.dtype) * (pred - gt).pow(2).sum(dim=2) / 2.0)     # model/utils.py:8-11 with a row mask
+
+    mcfg = synth.make_config("forward")["model"]
+    m = build("forward").double().train()
+    sd64 = {k: v.clone() for k, v in m.state_dict().items()}
+    # NB train-mode BatchNorm statistics do not depend on the queries, and the margins are taken in eval-agnostic fashion
+    # from a train-mode forward of the same weights: use the module itself for the margins' encoder by running the oracle
+    # in training mode on a copy of the buffers
+    kink = {}
+    with torch.no_grad():
+        orc.tdnet_forward({k: v.clone() for k, v in sd64.items()}, "", b3["space_samples_src"].double(),
+                          b3["surface_samples_inputs"].double(), mcfg, False, training=True, kink=kink)
+    keep = kink["margin"] > KINK
+    q = b3["space_samples_src"].double().clone().requires_grad_(True)
+    surf = b3["surface_samples_inputs"].double().clone().requires_grad_(True)
+    m.zero_grad()
+    pred = m(q, surf)
+    loss = masked_l2(pred, b3["space_samples_tgt"].double(), keep)
+    loss.backward()
+    gold["fw64_keep"] = keep.numpy()
+    gold["fw64_loss"] = np.array(loss.item(), np.float64)
+    gold["fw64_pred"] = pred.detach().numpy().astype(np.float32)
+    gold["fw64_dq"] = q.grad.numpy().astype(np.float32)
+    gold["fw64_dsurf"] = surf.grad.numpy().astype(np.float32)
+    m32 = build("forward").train()
+    m32.zero_grad()
+    q32 = b3["space_samples_src"].clone().requires_grad_(True)
+    s32 = b3["surface_samples_inputs"].clone().requires_grad_(True)
+    masked_l2(m32(q32, s32), b3["space_samples_tgt"], keep).backward()
+    gold["fw64_ref32err_dq"] = np.array(np.linalg.norm((q32.grad.numpy() - q.grad.numpy())[keep.numpy()]) / np.linalg.norm(q.grad.numpy()[keep.numpy()]))
+    gold["fw64_ref32err_dsurf"] = np.array(np.linalg.norm(s32.grad.numpy() - surf.grad.numpy()) / np.linalg.norm(surf.grad.numpy()))
+    dump_grads("fw64", m, twin32=m32)
+
+    # ---- 3. FlowArbitrary training step, STAGED (flow_arbitrary.py:15-27 written out so the stage boundary is visible) --
+    mcfg = synth.make_config("arbitrary")["model"]
+    b4 = synth.forward_batch(2, 640, 384, seed=9, fp16_grid=False)
+    s = b4["surface_samples_inputs"]
+    src, tgt, mask = s[:, :, 0:3].contiguous(), s[:, :, 3:6], s[:, :, 6:7]
+    # (a) stage 1 in fp32, exactly as the reference runs it (train mode): the coordinates every consumer teacher-forces
+    m32 = build("arbitrary").train()
+    with torch.no_grad():
+        space_c32 = m32.model_canonicalize(b4["space_samples_src"], src)
+        surf_c32 = m32.model_canonicalize(src, src)
+        pred32 = m32.model_deform(space_c32, torch.cat([surf_c32, tgt, mask], dim=-1).contiguous())
+    gold["arb_space_src2cano"] = space_c32.numpy()
+    gold["arb_surface_src2cano"] = surf_c32.numpy()
+    gold["arb_pred_fp32"] = pred32.numpy()
+    # (b) stage 2 in fp64, teacher-forced, masked loss
+    m = build("arbitrary").double().train()
+    sd64 = {k: v.clone() for k, v in m.state_dict().items()}
+    inp64 = torch.cat([surf_c32.double(), tgt.double(), mask.double()], dim=-1).contiguous()
+    kink = {}
+    with torch.no_grad():
+        orc.tdnet_forward({k: v.clone() for k, v in sd64.items()}, "model_deform.", space_c32.double(), inp64, mcfg, False,
+                          training=True, kink=kink)
+    keep2 = kink["margin"] > KINK
+    sp = space_c32.double().clone().requires_grad_(True)
+    su = surf_c32.double().clone().requires_grad_(True)
+    m.zero_grad()
+    pred = m.model_deform(sp, torch.cat([su, tgt.double(), mask.double()], dim=-1).contiguous())
+    loss = masked_l2(pred, b4["space_samples_tgt"].double(), keep2)
+    loss.backward()
+    gold["arb_keep2"] = keep2.numpy()
+    gold["arb_loss"] = np.array(loss.item(), np.float64)
+    gold["arb_pred"] = pred.detach().numpy().astype(np.float32)
+    gold["arb_d_space_src2cano"] = sp.grad.numpy().astype(np.float32)
+    gold["arb_d_surface_src2cano"] = su.grad.numpy().astype(np.float32)
+    m32.zero_grad()
+    sp32 = space_c32.clone().requires_grad_(True)
+    su32 = surf_c32.clone().requires_grad_(True)
+    masked_l2(m32.model_deform(sp32, torch.cat([su32, tgt, mask], dim=-1).contiguous()), b4["space_samples_tgt"], keep2).backward()
+    gold["arb_ref32err_d_surface"] = np.array(np.linalg.norm(su32.grad.numpy() - su.grad.numpy()) / np.linalg.norm(su.grad.numpy()))
+    dump_grads("arb2", m.model_deform, "model_deform.", twin32=m32.model_deform)
+    # (c) stage-1 backward in fp64, driven by (b)'s gradients with stage-1 kink rows zeroed
+    ks, kf = {}, {}
+    with torch.no_grad():
+        orc.tdnet_forward({k: v.clone() for k, v in sd64.items()}, "model_canonicalize.", b4["space_samples_src"].double(),
+                          src.double(), mcfg, True, training=True, kink=ks)
+        orc.tdnet_forward({k: v.clone() for k, v in sd64.items()}, "model_canonicalize.", src.double(), src.double(), mcfg,
+                          True, training=True, kink=kf)
+    keep1s, keep1f = ks["margin"] > KINK, kf["margin"] > KINK
+    up_s = torch.from_numpy(gold["arb_d_space_src2cano"]).double() * keep1s[..., None]
+    up_f = torch.from_numpy(gold["arb_d_surface_src2cano"]).double() * keep1f[..., None]
+    m.zero_grad()
+    space_c = m.model_canonicalize(b4["space_samples_src"].double(), src.double())
+    surf_c = m.model_canonicalize(src.double(), src.double())
+    torch.autograd.backward([space_c, surf_c], [up_s, up_f])
+    gold["arb_keep1_space"] = keep1s.numpy()
+    gold["arb_keep1_surface"] = keep1f.numpy()
+    m32.zero_grad()
+    torch.autograd.backward([m32.model_canonicalize(b4["space_samples_src"], src), m32.model_canonicalize(src, src)],
+                            [up_s.float(), up_f.float()])
+    dump_grads("arb1", m.model_canonicalize, "model_canonicalize.", twin32=m32.model_canonicalize)
+
+    np.savez_compressed(os.path.join(HERE, "tdnet_reference_r2.npz"), **gold)
+    print({k: v.shape for k, v in gold.items() if not k.startswith("arb_tr_grad::")})
+    print("bytes", os.path.getsize(os.path.join(HERE, "tdnet_reference_r2.npz")))
+
+
+if __name__ == "__main__":
+    main()

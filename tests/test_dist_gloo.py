@@ -91,6 +91,68 @@ def test_query_sharded_decode_world2():
         assert seen == [4]                     # ... having decoded only its (padded) slice
 
 
+def _mlp():
+    torch.manual_seed(11)
+    return torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                               torch.nn.Linear(16, 3), torch.nn.Linear(3, 3))     # the last layer is never used
+
+
+def _step_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      NSDP_B200_BUCKET_BYTES="256")          # tiny buckets: several collectives leave DURING backward
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(50 + rank)                              # replicas start different, as after a botched resume
+    model = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                                torch.nn.Linear(16, 3), torch.nn.Linear(3, 3))
+    if rank == 0:
+        model.load_state_dict(_mlp().state_dict())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    x = torch.randn(8, 4, generator=torch.Generator().manual_seed(1))
+    y = torch.randn(8, 3, generator=torch.Generator().manual_seed(2))
+    mine = nd.shard_batch({"x": x, "y": y})
+    launched_early = []
+    for step in range(3):
+        nd.zero_grad(model, opt)                               # first call: rank 0's weights/optimizer state become everybody's
+        bk = nd._buckets_for(model)
+        loss = (model[:5](mine["x"]) - mine["y"]).pow(2).mean()
+        loss.backward()
+        launched_early.append(bk.launched)                     # buckets already reduced/in flight when backward returns
+        nd.allreduce_gradients(model)
+        opt.step()
+    q.put((rank, {k: v.detach().numpy() for k, v in model.state_dict().items()}, launched_early, bk.nb,
+           all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bk.params, bk.views))))
+    td.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_matches_single_process_training_world2():
+    """3 Adam steps on 2 ranks x 4 rows == 3 steps of one process on the 8 rows; gradients live in the flat buffer; from the
+    second step on buckets leave during backward."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_step_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _mlp()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    x = torch.randn(8, 4, generator=torch.Generator().manual_seed(1))
+    y = torch.randn(8, 3, generator=torch.Generator().manual_seed(2))
+    for step in range(3):
+        opt.zero_grad()
+        (ref[:5](x) - y).pow(2).mean().backward()
+        opt.step()
+    for rank, sd, early, nb, views_ok in res:
+        assert views_ok and nb >= 3
+        assert early[0] == 0                       # step 1 learns which parameters get gradients: everything at the end
+        assert early[1] >= 1 and early[2] >= 1      # afterwards collectives leave while backward is still running
+        for k, v in ref.state_dict().items():
+            torch.testing.assert_close(torch.from_numpy(sd[k]), v, atol=1e-6, rtol=1e-5)
+
+
 def _net():
     torch.manual_seed(3)
     return torch.nn.Sequential(torch.nn.Linear(5, 6), torch.nn.BatchNorm1d(6), torch.nn.ReLU(), torch.nn.Linear(6, 2))

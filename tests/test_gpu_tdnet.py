@@ -90,20 +90,20 @@ def test_forward_full_size_shape_against_oracle(schemas):
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["fp32-cuda-cores", "auto-tcgen05"])
-def test_training_step_against_reference_golden(golden, schemas, impl, monkeypatch):
+def test_training_step_against_reference_golden(golden, golden_r2, schemas, impl, monkeypatch):
     """fwd + bwd through the CUDA kernels (train-mode BatchNorm): loss, prediction, d/d query coordinates,
-    d/d surface inputs, selected parameter gradients, all gradient norms and BN running stats vs the live
+    d/d surface inputs, selected parameter gradients, all gradient norms and BN running stats vs the live fp32
     reference (tests/golden/make_golden.py, 'train_fwd_*').
 
-    Gradient bar: relative L2 < 1e-3 on the fp32 CUDA-core kernels. The tensor-core kernels (bf16x3) reproduce
-    pre-activations to ~3e-6 instead of ~1e-7, which flips the ReLU mask of the few elements that sit within ~1e-5 of
-    the kink (tests/test_gpu_vattn.py::_tc_grad_ok; reproduced by a CPU emulation of the arithmetic); the gradients
-    that sum over those elements move by ~1e-3 (measured: d/d query 1.1e-3), so that path is held to 5e-3. The
-    forward tolerance (flow < 1e-4) is the same on both."""
+    Gradient bar: relative L2 < 1e-3 on BOTH kernel families. d/d query is compared on the queries that do
+    not sit on a ReLU kink (`fw64_keep`, the 70-odd % whose smallest decoder pre-activation is > 1e-4 of the layer rms):
+    a gradient is discontinuous there, and two fp32 implementations of the reference itself differ by 2e-3 on the full
+    tensor and by 1e-6 on the kept rows (tests/golden/make_golden_r2.py). The kink rows are excluded on both sides."""
     from nsdp_b200 import ops
     monkeypatch.setattr(ops, "VATTN_IMPL", impl)
     monkeypatch.setattr(ops, "TAIL_IMPL", impl)
-    gtol = 1e-3 if impl == 1 else 5e-3
+    gtol = 1e-3
+    keep = golden_r2["fw64_keep"]
     model = _model(schemas, "forward").train()
     b = synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
     q = b["space_samples_src"].to(DEV).requires_grad_(True)
@@ -115,7 +115,7 @@ def test_training_step_against_reference_golden(golden, schemas, impl, monkeypat
     assert abs(loss.item() - float(golden["train_fwd_loss"])) < 1e-5
     assert _mean_l2(pred.detach().cpu().numpy(), golden["train_fwd_pred"]) < TOL
     rel = lambda a, ref: float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30))
-    assert rel(q.grad.cpu().numpy(), golden["train_fwd_dq"]) < gtol
+    assert rel(q.grad.cpu().numpy()[keep], golden["train_fwd_dq"][keep]) < gtol
     assert rel(surf.grad.cpu().numpy(), golden["train_fwd_dsurf"]) < gtol
     grads = {k: p.grad for k, p in model.named_parameters()}
     for key in golden.files:
@@ -136,6 +136,103 @@ def test_training_step_against_reference_golden(golden, schemas, impl, monkeypat
             continue
         # parameters feeding straight into a BatchNorm (e.g. a bias) have a true gradient of 0: both sides are noise
         assert abs(a - r) <= 2 * gtol * r + 1e-7, (n, a, r)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-cuda-cores", "auto-tcgen05"])
+def test_training_step_every_gradient_against_fp64_truth(golden_r2, schemas, impl, monkeypatch):
+    """The same step against the fp64 run of the live reference, kink queries masked out of the LOSS on both sides
+    (make_golden_r2.py part 2): d/d query, d/d surface and EVERY parameter gradient within 1e-3 relative L2 (tensors kept
+    in full) / 1.5e-3 (seeded-projection estimate), or 3x the reference's own fp32 distance from the truth where that is
+    larger (ill-conditioned BatchNorm backward)."""
+    from helpers_r2 import check_param_grads, masked_l2, rel
+    from nsdp_b200 import ops
+    monkeypatch.setattr(ops, "VATTN_IMPL", impl)
+    monkeypatch.setattr(ops, "TAIL_IMPL", impl)
+    g = golden_r2
+    keep = g["fw64_keep"]
+    model = _model(schemas, "forward").train()
+    b = synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
+    q = b["space_samples_src"].to(DEV).requires_grad_(True)
+    surf = b["surface_samples_inputs"].to(DEV).requires_grad_(True)
+    pred = model(q, surf)
+    loss = masked_l2(pred, b["space_samples_tgt"].to(DEV), torch.from_numpy(keep).to(DEV))
+    loss.backward()
+    assert abs(loss.item() - float(g["fw64_loss"])) < 1e-5
+    assert _mean_l2(pred.detach().cpu().numpy(), g["fw64_pred"]) < TOL
+    e_dq = rel(q.grad.cpu().numpy()[keep], g["fw64_dq"][keep])
+    e_ds = rel(surf.grad.cpu().numpy(), g["fw64_dsurf"])
+    assert e_dq < 1e-3 and e_ds < 1e-3, (e_dq, e_ds)
+    grads = {k: (None if p.grad is None else p.grad.cpu().numpy()) for k, p in model.named_parameters()}
+    worst = check_param_grads(grads, g, "fw64", 1e-3, 1.5e-3)
+    print(f"[impl {impl}] d/dq {e_dq:.2e} (reference fp32: {float(g['fw64_ref32err_dq']):.2e}), d/dsurf {e_ds:.2e} "
+          f"(reference fp32: {float(g['fw64_ref32err_dsurf']):.2e}), worst parameter gradient {worst}")
+
+
+def test_flow_arbitrary_staged_training_step_against_fp64_truth(golden_r2, schemas):
+    """FlowArbitrary fwd+bwd stage by stage (make_golden_r2.py part 3): (a) stage 1 free-running vs the fp32 reference;
+    (b) stage 2 teacher-forced with the reference's stage-1 outputs vs fp64 truth: loss, prediction, the gradients that
+    reach the stage-1 outputs, every deform-net parameter gradient; (c) stage-1 backward driven by the truth's upstream
+    gradients: every canonicalise-net parameter gradient. Bars as in the test above."""
+    from helpers_r2 import check_param_grads, masked_l2, rel
+    g = golden_r2
+    model = _model(schemas, "arbitrary").train()
+    b = synth.forward_batch(2, 640, 384, seed=9, fp16_grid=False)
+    s = b["surface_samples_inputs"].to(DEV)
+    src, tgt, mask = s[:, :, 0:3].contiguous(), s[:, :, 3:6], s[:, :, 6:7]
+    cano, deform = model.model_canonicalize, model.model_deform
+    enc = cano.encode(src)
+    space_c = cano.decode(b["space_samples_src"].to(DEV), enc)
+    surf_c = cano.decode(src, enc)
+    assert _mean_l2(space_c.detach().cpu().numpy(), g["arb_space_src2cano"]) < TOL
+    assert _mean_l2(surf_c.detach().cpu().numpy(), g["arb_surface_src2cano"]) < TOL
+    space_in = torch.from_numpy(g["arb_space_src2cano"]).to(DEV).requires_grad_(True)
+    surf_in = torch.from_numpy(g["arb_surface_src2cano"]).to(DEV).requires_grad_(True)
+    pred = deform(space_in, torch.cat([surf_in, tgt, mask], -1).contiguous())
+    assert _mean_l2(pred.detach().cpu().numpy(), g["arb_pred"]) < TOL
+    keep2 = g["arb_keep2"]
+    loss = masked_l2(pred, b["space_samples_tgt"].to(DEV), torch.from_numpy(keep2).to(DEV))
+    assert abs(loss.item() - float(g["arb_loss"])) < 1e-5
+    loss.backward()
+    e_sp = rel(space_in.grad.cpu().numpy()[keep2], g["arb_d_space_src2cano"][keep2])
+    e_su = rel(surf_in.grad.cpu().numpy(), g["arb_d_surface_src2cano"])
+    assert e_sp < 1e-3 and e_su < max(1e-3, 3 * float(g["arb_ref32err_d_surface"])), (e_sp, e_su)
+    grads = {k: (None if p.grad is None else p.grad.cpu().numpy()) for k, p in model.named_parameters()
+             if k.startswith("model_deform.")}
+    w2 = check_param_grads(grads, g, "arb2", 1e-3, 1.5e-3)
+    up_s = torch.from_numpy(g["arb_d_space_src2cano"] * g["arb_keep1_space"][..., None]).to(DEV)
+    up_f = torch.from_numpy(g["arb_d_surface_src2cano"] * g["arb_keep1_surface"][..., None]).to(DEV)
+    torch.autograd.backward([space_c, surf_c], [up_s, up_f])
+    grads = {k: (None if p.grad is None else p.grad.cpu().numpy()) for k, p in model.named_parameters()
+             if k.startswith("model_canonicalize.")}
+    w1 = check_param_grads(grads, g, "arb1", 1e-3, 1.5e-3)
+    print(f"stage 2: d/d space {e_sp:.2e}, d/d surface {e_su:.2e}, worst deform gradient {w2}; stage 1: worst {w1}")
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_encoder_per_block_activations_against_reference(golden_r2, schemas, mode):
+    """the output of every encoder block (transformer_begin, each TransitionDown / ElementwiseMLP /
+    TransformerBlock, the three final blocks) against forward-hook captures of the live reference
+    (make_golden_r2.py part 1) — eval mode on the C1 cloud, train mode (batch-statistics BatchNorm) on the training batch."""
+    from helpers_r2 import rel, thin
+    model = _model(schemas, "forward")
+    model = model.eval() if mode == "eval" else model.train()
+    b = synth.forward_batch(1, 1024, 2048, seed=1234, fp16_grid=False) if mode == "eval" else \
+        synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
+    got, hooks = {}, []
+    for name, mod in model.encoder.named_modules():
+        if f"trace_{mode}::{name}" in golden_r2.files:
+            def hook(_m, _i, o, name=name):
+                got[name] = thin((o[1] if isinstance(o, tuple) else o).detach().cpu().numpy())
+            hooks.append(mod.register_forward_hook(hook))
+    with torch.no_grad():
+        model.encoder(b["surface_samples_inputs"].to(DEV))
+    for h in hooks:
+        h.remove()
+    keys = [k.split("::", 1)[1] for k in golden_r2.files if k.startswith(f"trace_{mode}::")]
+    assert len(keys) == 15 and set(keys) == set(got)
+    for k in keys:
+        e = rel(got[k], golden_r2[f"trace_{mode}::{k}"])
+        assert e < 1e-4, (k, e)
 
 
 def test_flow_arbitrary_training_step(golden, schemas):

@@ -32,6 +32,7 @@ def test_per_rank_seed_and_output_directory(tmp_path):
     from nsdp_b200 import launch
     cfg = tmp_path / "forward.yaml"
     cfg.write_text(yaml.safe_dump({"experiment": {"out_dir": "/data/out", "name": "run"}, "model": {"type": "forward"}}))
+    cfg.write_text(yaml.safe_dump({"experiment": {"out_dir": str(tmp_path / "out"), "name": "run"}, "model": {"type": "forward"}}))
     argv = ["/repo/NSDP/train.py", str(cfg), "--num_workers", "4"]
     assert launch.rewrite_argv_for_rank(argv, 0, 1, str(tmp_path)) == argv                       # single process: untouched
     r0 = launch.rewrite_argv_for_rank(argv, 0, 8, str(tmp_path / "s"))
@@ -39,6 +40,29 @@ def test_per_rank_seed_and_output_directory(tmp_path):
     r3 = launch.rewrite_argv_for_rank(argv + ["--seed", "100"], 3, 8, str(tmp_path / "s"))
     assert r3[-2:] == ["--seed", "103"] and r3.count("--seed") == 1 and r3[2:4] == ["--num_workers", "4"]
     got = yaml.safe_load(open(r3[1]))
-    assert got["experiment"] == {"out_dir": "/data/out/rank3", "name": "run"} and got["model"] == {"type": "forward"}
+    assert got["experiment"] == {"out_dir": str(tmp_path / "out" / "rank3"), "name": "run"} and got["model"] == {"type": "forward"}
     test_argv = ["/repo/NSDP/test.py", str(cfg)]
     assert launch.rewrite_argv_for_rank(test_argv, 3, 8, str(tmp_path)) == test_argv              # only train.py writes checkpoints
+
+
+def test_resume_reads_rank0_checkpoints_on_every_rank(tmp_path):
+    """ranks > 0 must not resume from their own (stale / missing) files: their private experiment directory
+    starts as links to rank 0's model_* / opt_* / modelbest_* files, so load_checkpoints (utils/checkpoints.py:8-31)
+    picks the same epoch and weights everywhere."""
+    import os
+    import yaml
+    from nsdp_b200 import launch
+    shared = tmp_path / "out" / "run"
+    shared.mkdir(parents=True)
+    for f in ("model_00020", "opt_00020", "modelbest_00010_0.123000", "stats.txt"):
+        (shared / f).write_text(f)
+    stale = tmp_path / "out" / "rank1" / "run"
+    stale.mkdir(parents=True)
+    (stale / "model_00040").write_text("from an older 2-rank run")
+    (stale / "opt_00040").write_text("x")
+    cfg = tmp_path / "forward.yaml"
+    cfg.write_text(yaml.safe_dump({"experiment": {"out_dir": str(tmp_path / "out"), "name": "run"}}))
+    launch.rewrite_argv_for_rank(["/repo/NSDP/train.py", str(cfg)], 1, 2, str(tmp_path / "s"))
+    names = sorted(os.listdir(stale))
+    assert names == ["model_00020", "modelbest_00010_0.123000", "opt_00020"]
+    assert (stale / "model_00020").read_text() == "model_00020" and os.path.islink(stale / "opt_00020")
