@@ -30,12 +30,14 @@ def install_aliases() -> None:
     sys.modules["pointnet2_ops"] = p2
     sys.modules["pointnet2_ops._ext"] = p2._ext
     sys.modules["pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
+    sys.modules["pointnet2_ops.pointnet2_modules"] = p2.pointnet2_modules
     lib = types.ModuleType("pointnet2_ops_lib")
     lib.pointnet2_ops = p2
     lib.__path__ = []
     sys.modules["pointnet2_ops_lib"] = lib
     sys.modules["pointnet2_ops_lib.pointnet2_ops"] = p2
     sys.modules["pointnet2_ops_lib.pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
+    sys.modules["pointnet2_ops_lib.pointnet2_ops.pointnet2_modules"] = p2.pointnet2_modules
 
 
 def mirror_checkpoints(shared_dir: str, private_dir: str) -> None:

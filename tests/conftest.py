@@ -9,6 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))       # tests/helpers (harness), tests/helpers_r2.py
+
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 

@@ -1,0 +1,121 @@
+"""B1 boundary beyond FPS: the autograd wrappers of nsdp_b200/pointnet2_ops/pointnet2_utils.py and
+the SA / FP modules of pointnet2_modules.py against the REFERENCE's own Python files (baseline/_ref copy of
+pointnet2_ops_lib/pointnet2_ops/*.py) running on the reference's own CUDA extension (oracle/_ref, built from the
+unmodified sources for sm_100a). Forward values and index tensors bit-exact; scatter-add gradients to fp32 rounding."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from baseline import ref_loader
+    from oracle import ref_ext
+    if not ref_loader.available() or ref_ext.load() is None:
+        pytest.skip("baseline/_ref or oracle/_ref not present (built where /root/reference exists)")
+    ref_loader.load()
+    import pointnet2_ops.pointnet2_modules as rm    # the reference's files, bound to the reference's extension
+    import pointnet2_ops.pointnet2_utils as ru
+    assert "baseline/_ref" in rm.__file__ and "baseline/_ref" in ru.__file__
+    return ru, rm
+
+
+@pytest.fixture(scope="module")
+def ours():
+    from nsdp_b200.pointnet2_ops import pointnet2_modules as om
+    from nsdp_b200.pointnet2_ops import pointnet2_utils as ou
+    return ou, om
+
+
+def _cloud(B, N, seed, C=0):
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(B, N, 3, generator=g) - 0.5).to(DEV)
+    feats = torch.randn(B, C, N, generator=g).to(DEV) if C else None
+    return xyz, feats
+
+
+def test_wrappers_forward_and_backward(ref, ours):
+    ru, _ = ref
+    ou, _ = ours
+    xyz, feats = _cloud(3, 700, 1, C=6)
+    idx_r = ru.furthest_point_sample(xyz, 64)
+    idx_o = ou.furthest_point_sample(xyz, 64)
+    assert idx_o.dtype == torch.int32 and torch.equal(idx_r, idx_o) and not idx_o.requires_grad
+    # gather_operation: values bit-exact, gradient = scatter-add
+    f_r, f_o = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+    g_r, g_o = ru.gather_operation(f_r, idx_r), ou.gather_operation(f_o, idx_o)
+    assert torch.equal(g_r, g_o)
+    up = torch.randn_like(g_r)
+    g_r.backward(up)
+    g_o.backward(up)
+    torch.testing.assert_close(f_o.grad, f_r.grad, atol=1e-6, rtol=1e-6)
+    # ball query + grouping (QueryAndGroup), with and without features
+    new_xyz = ou.gather_operation(xyz.transpose(1, 2).contiguous(), idx_o).transpose(1, 2).contiguous()
+    for use_xyz in (True, False):
+        f_r, f_o = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+        q_r = ru.QueryAndGroup(0.15, 24, use_xyz=use_xyz)(xyz, new_xyz, f_r)
+        q_o = ou.QueryAndGroup(0.15, 24, use_xyz=use_xyz)(xyz, new_xyz, f_o)
+        assert q_o.shape == q_r.shape and torch.equal(q_r, q_o)
+        up = torch.randn_like(q_r)
+        q_r.backward(up)
+        q_o.backward(up)
+        torch.testing.assert_close(f_o.grad, f_r.grad, atol=2e-6, rtol=1e-5)
+    assert torch.equal(ru.QueryAndGroup(0.15, 24)(xyz, new_xyz, None), ou.QueryAndGroup(0.15, 24)(xyz, new_xyz, None))
+    assert torch.equal(ru.ball_query(0.15, 24, xyz, new_xyz), ou.ball_query(0.15, 24, xyz, new_xyz))
+    assert torch.equal(ru.GroupAll()(xyz, None, feats), ou.GroupAll()(xyz, None, feats))
+    # 3-NN + interpolation
+    d_r, i_r = ru.three_nn(xyz, new_xyz)
+    d_o, i_o = ou.three_nn(xyz, new_xyz)
+    assert torch.equal(i_r, i_o) and torch.equal(d_r, d_o)
+    w = torch.softmax(torch.randn(3, 700, 3, device=DEV), dim=-1)
+    kf = torch.randn(3, 9, 64, device=DEV)
+    k_r, k_o = kf.clone().requires_grad_(True), kf.clone().requires_grad_(True)
+    t_r, t_o = ru.three_interpolate(k_r, i_r, w), ou.three_interpolate(k_o, i_o, w)
+    assert torch.equal(t_r, t_o)
+    up = torch.randn_like(t_r)
+    t_r.backward(up)
+    t_o.backward(up)
+    torch.testing.assert_close(k_o.grad, k_r.grad, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_sa_and_fp_modules_against_reference_modules(ref, ours, train):
+    _, rm = ref
+    _, om = ours
+    torch.manual_seed(3)
+    xyz, feats = _cloud(2, 600, 5, C=4)
+    specs = dict(npoint=48, radii=[0.12, 0.3], nsamples=[8, 20], mlps=[[4, 16, 24], [4, 16, 32]])
+    import copy
+    m_r = rm.PointnetSAModuleMSG(**copy.deepcopy(specs)).to(DEV)
+    m_o = om.PointnetSAModuleMSG(**copy.deepcopy(specs)).to(DEV)
+    assert list(m_r.state_dict().keys()) == list(m_o.state_dict().keys())
+    m_o.load_state_dict(m_r.state_dict())
+    single_r = rm.PointnetSAModule(mlp=[24 + 32, 40], npoint=None).to(DEV)      # group-all scale
+    single_o = om.PointnetSAModule(mlp=[24 + 32, 40], npoint=None).to(DEV)
+    single_o.load_state_dict(single_r.state_dict())
+    fp_r = rm.PointnetFPModule(mlp=[56 + 4, 32, 16]).to(DEV)
+    fp_o = om.PointnetFPModule(mlp=[56 + 4, 32, 16]).to(DEV)
+    fp_o.load_state_dict(fp_r.state_dict())
+    for m in (m_r, m_o, single_r, single_o, fp_r, fp_o):
+        m.train(train)
+    outs = []
+    for sa, single, fp in ((m_r, single_r, fp_r), (m_o, single_o, fp_o)):
+        f = feats.clone().requires_grad_(True)
+        new_xyz, nf = sa(xyz, f)                       # (B,48,3), (B,56,48)
+        none_xyz, glob = single(new_xyz, nf)           # None, (B,40,1)
+        back = fp(xyz, new_xyz, f, nf)                 # (B,16,600)
+        (back.square().mean() + glob.square().mean()).backward()
+        outs.append((new_xyz, nf, none_xyz, glob, back, f.grad, sa.mlps[0][0].weight.grad, fp.mlp[0].weight.grad))
+    (x_r, nf_r, n_r, g_r, b_r, df_r, dw_r, dfp_r), (x_o, nf_o, n_o, g_o, b_o, df_o, dw_o, dfp_o) = outs
+    assert n_r is None and n_o is None and torch.equal(x_r, x_o)
+    torch.testing.assert_close(nf_o, nf_r, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(g_o, g_r, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(b_o, b_r, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(df_o, df_r, atol=1e-6, rtol=1e-4)
+    torch.testing.assert_close(dw_o, dw_r, atol=1e-6, rtol=1e-4)
+    torch.testing.assert_close(dfp_o, dfp_r, atol=1e-6, rtol=1e-4)
