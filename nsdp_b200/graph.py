@@ -1,0 +1,130 @@
+"""Whole-step CUDA graphs behind the unchanged train_on_batch_* API.
+
+A training step of this model is ~1100 kernel launches, most of them microsecond-sized encoder glue; issued one by one
+from Python + autograd they leave the GPU idle for milliseconds per step. All shapes are static from step to step
+(fixed batch, fixed point counts), there is no host synchronisation between `zero_grad` and `loss.item()`, and every
+nsdp_b200 kernel is launched on the current stream through the C ABI — so the WHOLE step (forward, loss, backward, fused
+Adam) is captured once into a CUDA graph and replayed: one launch per step.
+
+    step = graphed_train_step(model, optimizer, data_dict, eager_fn)      # -> float loss, same as eager_fn(...)
+
+Protocol per (model, optimizer, input shapes): the first WARMUP calls run eagerly on a side stream (lazy initialisation:
+cuBLAS handles, kernel attributes, gradient buffers, Adam state), the next call captures, later calls copy the batch into
+the graph's static input buffers and replay. Anything that prevents capture (non-capturable optimizer, a failed capture,
+a process group: NCCL calls from autograd hooks are not captured) falls back to the eager path, loudly, once.
+The learning rate is read from the param groups on every call; a change (model/learningrate.py adjust_learning_rate,
+train.py:188) re-captures, because a Python float lr is baked into the captured launch.
+NSDP_B200_GRAPH=0 disables the whole mechanism.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import weakref
+
+import torch
+
+from nsdp_b200 import ops
+
+ENABLED = os.environ.get("NSDP_B200_GRAPH", "1") != "0"
+WARMUP = 3
+_STATE = weakref.WeakKeyDictionary()      # model -> {signature: _Entry}
+
+
+class _Entry:
+    __slots__ = ("calls", "graph", "static", "loss", "lrs", "launches", "failed", "opt_ref")
+
+    def __init__(self):
+        self.calls, self.graph, self.static, self.loss = 0, None, None, None
+        self.lrs, self.launches, self.failed, self.opt_ref = None, 0, False, None
+
+
+def _signature(model, optimizer, data_dict):
+    sig = [id(optimizer), model.training]
+    for k in sorted(data_dict):
+        v = data_dict[k]
+        if torch.is_tensor(v):
+            sig.append((k, tuple(v.shape), v.dtype, str(v.device)))
+    return tuple(sig)
+
+
+def _lrs(optimizer):
+    out = []
+    for g in optimizer.param_groups:
+        lr = g["lr"]
+        out.append(float(lr) if not torch.is_tensor(lr) else None)      # a tensor lr lives on the device: no re-capture
+        out.append(float(g.get("weight_decay", 0.0)))
+    return tuple(out)
+
+
+def _capturable(optimizer) -> bool:
+    return isinstance(optimizer, torch.optim.Adam) and all(g.get("capturable", False) for g in optimizer.param_groups)
+
+
+def _usable(model, optimizer, data_dict) -> bool:
+    if not ENABLED or ops.TIMING:
+        return False
+    from nsdp_b200 import dist
+    if dist.is_active():
+        return False
+    if not _capturable(optimizer):
+        return False
+    tensors = [v for v in data_dict.values() if torch.is_tensor(v)]
+    return bool(tensors) and all(v.is_cuda for v in tensors) and not torch.cuda.is_current_stream_capturing()
+
+
+def graphed_train_step(model, optimizer, data_dict, eager_fn):
+    """eager_fn(model, optimizer, data_dict) -> loss TENSOR (zero_grad + forward + loss + backward + step, no .item())."""
+    if not _usable(model, optimizer, data_dict):
+        return eager_fn(model, optimizer, data_dict).item()
+    per_model = _STATE.setdefault(model, {})
+    sig = _signature(model, optimizer, data_dict)
+    e = per_model.get(sig)
+    if e is None:
+        e = per_model[sig] = _Entry()
+    if e.failed:
+        return eager_fn(model, optimizer, data_dict).item()
+    lrs = _lrs(optimizer)
+    if e.graph is not None and e.lrs != lrs:
+        e.graph, e.static, e.loss = None, None, None           # learning rate changed: capture again
+    if e.graph is None:
+        if e.calls < WARMUP:
+            e.calls += 1
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                loss = eager_fn(model, optimizer, data_dict)
+            torch.cuda.current_stream().wait_stream(side)
+            return loss.item()
+        try:
+            _capture(e, model, optimizer, data_dict, eager_fn)
+            e.lrs = lrs
+        except Exception as exc:   # noqa: BLE001 — never lose a training step over an optimisation
+            e.failed = True
+            e.graph = None
+            torch.cuda.synchronize()
+            print(f"[nsdp_b200.graph] CUDA-graph capture of the training step failed ({type(exc).__name__}: {exc}); "
+                  "continuing on the eager path", file=sys.stderr)
+            return eager_fn(model, optimizer, data_dict).item()
+    for k, buf in e.static.items():
+        src = data_dict[k]
+        if src.data_ptr() != buf.data_ptr():
+            buf.copy_(src, non_blocking=True)
+    e.graph.replay()
+    ops._count(e.launches)
+    return e.loss.item()
+
+
+def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
+    static = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
+    passthrough = {k: v for k, v in data_dict.items() if not torch.is_tensor(v)}
+    # gradients must be (re)created INSIDE the capture so that they live in the graph's memory pool
+    optimizer.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    before = ops.LAUNCHES
+    with torch.cuda.graph(g):
+        loss = eager_fn(model, optimizer, {**static, **passthrough})
+    e.launches = ops.LAUNCHES - before
+    e.graph, e.static, e.loss = g, static, loss
+    # the capture itself executed nothing: the caller replays right away with the current batch

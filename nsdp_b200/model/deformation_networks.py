@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from nsdp_b200 import dist as nsdp_dist
+from nsdp_b200.graph import graphed_train_step
 from nsdp_b200.model.decoder import decoder_dict
 from nsdp_b200.model.encoder import encoder_dict
 from nsdp_b200.model.utils import compute_l2_error
@@ -44,14 +45,20 @@ class Deformation_Networks(nn.Module):
         return self.decode(points, self.encode(surface_samples_inputs))
 
 
-def train_on_batch_with_cano(model, optimizer, data_dict, config):
+def _train_step_with_cano(model, optimizer, data_dict):
     nsdp_dist.zero_grad(model, optimizer)
     pred = model(data_dict["space_samples_src"], data_dict["surface_samples_inputs"])
     loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
     loss.backward()
     nsdp_dist.allreduce_gradients(model)
     optimizer.step()
-    return loss.item()
+    return loss
+
+
+def train_on_batch_with_cano(model, optimizer, data_dict, config):
+    """deformation_networks.py:63-77. The step itself is `_train_step_with_cano`; on a GPU it is captured into a CUDA graph
+    after a few calls and replayed (nsdp_b200/graph.py) — same arithmetic, one launch per step."""
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_cano)
 
 
 @torch.no_grad()

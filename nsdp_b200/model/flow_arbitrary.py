@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from nsdp_b200 import dist as nsdp_dist
+from nsdp_b200.graph import graphed_train_step
 from nsdp_b200.model.utils import compute_l2_error
 
 
@@ -63,7 +64,7 @@ def _split_inputs(data_dict):
     return s[:, :, 0:3], s[:, :, 3:6], s[:, :, 6:7]
 
 
-def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
+def _train_step_with_arbitrary(model, optimizer, data_dict):
     nsdp_dist.zero_grad(model, optimizer)
     src, tgt, mask = _split_inputs(data_dict)
     pred = model(data_dict["space_samples_src"], src, tgt, mask)
@@ -71,7 +72,12 @@ def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
     loss.backward()
     nsdp_dist.allreduce_gradients(model)
     optimizer.step()
-    return loss.item()
+    return loss
+
+
+def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
+    """flow_arbitrary.py:30-48; captured into a CUDA graph after a few calls (nsdp_b200/graph.py)."""
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_arbitrary)
 
 
 @torch.no_grad()

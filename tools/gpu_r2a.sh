@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, first GPU call: the whole -m gpu suite without -x (see everything that fails), smoke, bench with the new reference arms
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
+timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+grep -E "passed|failed|FAILED|ERROR|worst|d/dq|stage 2" gpurun_out/pytest_gpu.log | tail -40
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v Warn | tail -2
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 1500 gpurun_out/bench.json
+tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; echo "reference rc=$?"
+tail -c 900 gpurun_out/bench_reference.json
