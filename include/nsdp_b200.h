@@ -262,6 +262,42 @@ size_t nsdp_fused_mlp_bwd_workspace_bytes(const nsdp_mlp_args *args);
 int nsdp_fused_mlp_bwd_f32(const nsdp_mlp_args *args, const float *d_out /* (R,O) */, const nsdp_mlp_grads *grads,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* ElementwiseMLP of the point-transformer encoder (model/encoder/blocks.py:137-159):
+ *     out = bn3( x + relu( bn2( conv2( relu( bn1( conv1 x ) ) ) ) ) )
+ * over rows x (R, C) = the (B, n, C) feature tensor; conv1 / conv2 are the kernel-size-1 Conv1d layers (weights (C, C)
+ * = [out][in], biases (C)), bn1..bn3 nn.BatchNorm1d(C). Replaces the reference's permute -> 2 cuDNN convolutions ->
+ * 3 cuDNN batch-norms -> 2 ReLUs -> add chain (~12 launches forward, ~30 backward) by 4 + 7 fused fp32 kernels
+ * (csrc/emlp.cu). training != 0: batch statistics (biased variance) and in-place running-stat updates exactly as
+ * nn.BatchNorm1d (momentum, unbiased running_var, num_batches_tracked += 1); training == 0: running statistics.
+ * C <= 256. The forward also returns what the backward needs: t1 = conv1(x), t2 = conv2(relu(bn1 t1)), s = x + relu(bn2 t2)
+ * (R, C each) and `stats`, nsdp_emlp_stats_bytes() bytes of fp64 column sums (sum, sum of squares of t1, t2, s). */
+typedef struct {
+  const float *x;                       /* (R, C) */
+  const float *w1, *b1, *w2, *b2;       /* conv1 / conv2: (C, C) [out][in], (C) */
+  const float *bn_weight[3], *bn_bias[3];
+  float *running_mean[3], *running_var[3];     /* updated in place when training */
+  long long *num_batches_tracked[3];           /* int64 scalars, incremented when training (may be NULL) */
+  int R, C;
+  int training;
+  float momentum, eps;
+} nsdp_emlp_args;
+
+size_t nsdp_emlp_stats_bytes(const nsdp_emlp_args *args);
+int nsdp_emlp_fwd_f32(const nsdp_emlp_args *args, float *out, float *t1, float *t2, float *s, double *stats, void *stream);
+
+/* Backward: d_x (R, C) is overwritten; d_w1 / d_w2 (C, C) and d_b1 / d_b2 (C) ACCUMULATE (pass zero-filled buffers);
+ * d_bn_weight / d_bn_bias (C each) are overwritten and may be NULL. Both modes (batch / running statistics). */
+typedef struct {
+  float *d_x;
+  float *d_w1, *d_b1, *d_w2, *d_b2;
+  float *d_bn_weight[3], *d_bn_bias[3];
+} nsdp_emlp_grads;
+
+size_t nsdp_emlp_bwd_workspace_bytes(const nsdp_emlp_args *args);
+int nsdp_emlp_bwd_f32(const nsdp_emlp_args *args, const float *t1, const float *t2, const float *s, const double *stats,
+                      const float *d_out, const nsdp_emlp_grads *grads, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
  * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.

@@ -62,6 +62,20 @@ class MlpGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_x", "d_w_in_t", "d_b_in", "d_w_h_t", "d_b_h", "d_w_out_t", "d_b_out")]
 
 
+class EmlpArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("bn_weight", C.c_void_p * 3), ("bn_bias", C.c_void_p * 3),
+        ("running_mean", C.c_void_p * 3), ("running_var", C.c_void_p * 3), ("num_batches_tracked", C.c_void_p * 3),
+        ("R", C.c_int), ("C", C.c_int), ("training", C.c_int), ("momentum", C.c_float), ("eps", C.c_float),
+    ]
+
+
+class EmlpGrads(C.Structure):
+    _fields_ = [("d_x", C.c_void_p), ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p),
+                ("d_bn_weight", C.c_void_p * 3), ("d_bn_bias", C.c_void_p * 3)]
+
+
 # name -> (restype, argtypes); must list every symbol include/nsdp_b200.h declares
 # (tests/test_abi.py cross-checks this table against the header).
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -94,6 +108,10 @@ SIGNATURES = {
     "nsdp_fused_mlp_fwd_f32": (_I, [C.POINTER(MlpArgs), _P, _P, _SZ, _P]),
     "nsdp_fused_mlp_bwd_workspace_bytes": (_SZ, [C.POINTER(MlpArgs)]),
     "nsdp_fused_mlp_bwd_f32": (_I, [C.POINTER(MlpArgs), _P, C.POINTER(MlpGrads), _P, _SZ, _P]),
+    "nsdp_emlp_stats_bytes": (_SZ, [C.POINTER(EmlpArgs)]),
+    "nsdp_emlp_fwd_f32": (_I, [C.POINTER(EmlpArgs), _P, _P, _P, _P, _P, _P]),
+    "nsdp_emlp_bwd_workspace_bytes": (_SZ, [C.POINTER(EmlpArgs)]),
+    "nsdp_emlp_bwd_f32": (_I, [C.POINTER(EmlpArgs), _P, _P, _P, _P, _P, C.POINTER(EmlpGrads), _P, _SZ, _P]),
     "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 

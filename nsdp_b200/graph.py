@@ -123,6 +123,11 @@ def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     before = ops.LAUNCHES
+    # the parameters' AccumulateGrad nodes were created on the warm-up stream; inside the capture everything runs on the
+    # capture stream, which is what is wanted here
+    warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if warn is not None:
+        warn(False)
     with torch.cuda.graph(g):
         loss = eager_fn(model, optimizer, {**static, **passthrough})
     e.launches = ops.LAUNCHES - before

@@ -104,9 +104,8 @@ class ElementwiseMLP(nn.Module):
         self.bn3 = nn.BatchNorm1d(dim)
 
     def forward(self, x):
-        h = F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, x)))
-        h = F.relu(_bn_rows(self.bn2, _pointwise(self.conv2, h)))
-        return _bn_rows(self.bn3, x + h)
+        # one fused op: 4 kernels forward / 7 backward (csrc/emlp.cu) instead of the ~12 / ~30 cuDNN + elementwise launches
+        return ops.elementwise_mlp(x, self.conv1, self.bn1, self.conv2, self.bn2, self.bn3)
 
 
 class TransformerSetAbstraction(nn.Module):

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MlpArgs, MlpGrads, TailArgs, TailGrads, VattnArgs, VattnGrads, check
+from ._lib import EmlpArgs, EmlpGrads, MlpArgs, MlpGrads, TailArgs, TailGrads, VattnArgs, VattnGrads, check
 
 LAUNCHES = 0  # number of libnsdp_b200 kernel-launching calls made (bench.py reports it)
 
@@ -398,6 +398,84 @@ class _ResnetTail(torch.autograd.Function):
 def resnet_tail(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
     """Fused decoder ResNet-FC tail over rows: (R,C) -> (R,O). See nsdp_tail_args."""
     return _ResnetTail.apply(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ElementwiseMLP of the encoder (model/encoder/blocks.py:137-159): conv1 -> bn1 -> relu -> conv2 -> bn2 -> relu -> +x -> bn3
+# ---------------------------------------------------------------------------------------------------
+def _emlp_args(x2d, w1, b1, w2, b2, bns, training: bool) -> EmlpArgs:
+    a = EmlpArgs()
+    a.x, a.w1, a.b1, a.w2, a.b2 = _p(x2d), _p(w1), _p(b1), _p(w2), _p(b2)
+    for i, bn in enumerate(bns):
+        a.bn_weight[i], a.bn_bias[i] = _p(bn.weight), _p(bn.bias)
+        a.running_mean[i], a.running_var[i] = _p(bn.running_mean), _p(bn.running_var)
+        a.num_batches_tracked[i] = _p(bn.num_batches_tracked)
+    a.R, a.C = x2d.shape
+    a.training = 1 if training else 0
+    a.momentum = float(bns[0].momentum)
+    a.eps = float(bns[0].eps)
+    return a
+
+
+class _ElementwiseMLP(torch.autograd.Function):
+    """forward = nsdp_emlp_fwd_f32 (4 kernels), backward = nsdp_emlp_bwd_f32 (7 kernels). The three BatchNorm modules are
+    passed as a non-tensor argument: their running buffers are updated in place by the forward, like F.batch_norm does."""
+
+    @staticmethod
+    def forward(ctx, x2d, w1, b1, w2, b2, g1, be1, g2, be2, g3, be3, bns, training):
+        for n, t in dict(x=x2d, w1=w1, b1=b1, w2=w2, b2=b2, g1=g1, be1=be1, g2=g2, be2=be2, g3=g3, be3=be3).items():
+            _chk_f32(n, t)
+        a = _emlp_args(x2d, w1, b1, w2, b2, bns, training)
+        dev = x2d.device
+        out, t1, t2, s = (torch.empty_like(x2d) for _ in range(4))
+        L = _lib.lib()
+        stats = torch.empty((L.nsdp_emlp_stats_bytes(C.byref(a)) // 8,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev), _timed(f"emlp_fwd_R{a.R}_C{a.C}"):
+            check(L.nsdp_emlp_fwd_f32(C.byref(a), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), s.data_ptr(), stats.data_ptr(),
+                                      _stream()), "nsdp_emlp_fwd_f32")
+        _count()
+        ctx.bns, ctx.training = bns, training
+        ctx.save_for_backward(x2d, w1, b1, w2, b2, t1, t2, s, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x2d, w1, b1, w2, b2, t1, t2, s, stats = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        a = _emlp_args(x2d, w1, b1, w2, b2, ctx.bns, ctx.training)
+        Cc, dev = a.C, x2d.device
+        d_x = torch.empty_like(x2d)
+        flat = torch.zeros((2 * Cc * Cc + 8 * Cc,), dtype=torch.float32, device=dev)     # one memset for every gradient
+        d_w1, d_w2 = flat[:Cc * Cc].view(Cc, Cc), flat[Cc * Cc:2 * Cc * Cc].view(Cc, Cc)
+        small = flat[2 * Cc * Cc:].view(8, Cc)          # d_b1, d_b2, d_gamma1..3, d_beta1..3
+        g = EmlpGrads()
+        g.d_x, g.d_w1, g.d_w2, g.d_b1, g.d_b2 = d_x.data_ptr(), d_w1.data_ptr(), d_w2.data_ptr(), small[0].data_ptr(), small[1].data_ptr()
+        for i in range(3):
+            g.d_bn_weight[i], g.d_bn_bias[i] = small[2 + i].data_ptr(), small[5 + i].data_ptr()
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ws_bytes = L.nsdp_emlp_bwd_workspace_bytes(C.byref(a))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            with _timed(f"emlp_bwd_R{a.R}_C{a.C}"):
+                check(L.nsdp_emlp_bwd_f32(C.byref(a), t1.data_ptr(), t2.data_ptr(), s.data_ptr(), stats.data_ptr(),
+                                          d_out.data_ptr(), C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nsdp_emlp_bwd_f32")
+        _count()
+        return (d_x, d_w1, small[0], d_w2, small[1], small[2], small[5], small[3], small[6], small[4], small[7], None, None)
+
+
+def elementwise_mlp(x, conv1, bn1, conv2, bn2, bn3):
+    """bn3(x + relu(bn2(conv2(relu(bn1(conv1 x)))))) over the rows of x (B, n, C); the arguments are the nn.Conv1d /
+    nn.BatchNorm1d modules of the reference's ElementwiseMLP (their parameters get gradients, their buffers are updated)."""
+    B, n, Cc = x.shape
+    for bn in (bn1, bn2, bn3):
+        if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+            raise NotImplementedError("ElementwiseMLP kernel: BatchNorm1d with affine=True, track_running_stats=True and a "
+                                      "fixed momentum (the reference's defaults, model/encoder/blocks.py:148-151)")
+    training = bn1.training
+    out = _ElementwiseMLP.apply(x.reshape(B * n, Cc).contiguous(), conv1.weight.squeeze(-1), conv1.bias,
+                                conv2.weight.squeeze(-1), conv2.bias, bn1.weight, bn1.bias, bn2.weight, bn2.bias,
+                                bn3.weight, bn3.bias, (bn1, bn2, bn3), training)
+    return out.reshape(B, n, Cc)
 
 
 # ---------------------------------------------------------------------------------------------------

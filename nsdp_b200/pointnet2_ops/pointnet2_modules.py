@@ -13,6 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from nsdp_b200.pointnet2_ops import pointnet2_utils as pu
 
@@ -48,7 +49,8 @@ class _PointnetSAModuleBase(nn.Module):
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
             grouped = mlp(grouper(xyz, new_xyz, features))                          # (B, mlp[-1], npoint, nsample)
-            pooled.append(grouped.amax(dim=3))                                      # max over the neighbourhood
+            # max over the neighbourhood; max_pool2d (not amax) so that ties route their gradient exactly as in the reference
+            pooled.append(F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)]).squeeze(-1))
         return new_xyz, torch.cat(pooled, dim=1)
 
 

@@ -119,6 +119,6 @@ def test_sa_and_fp_modules_against_reference_modules(ref, ours, train):
     # gradients: relative L2 (train-mode BatchNorm statistics come out of order-nondeterministic reductions on BOTH
     # sides, a 1e-7 difference flips a few ReLU masks, and single elements then differ at the 1e-5 level)
     rel = lambda a, b: float((a - b).norm() / b.norm())
-    tol = 2e-3 if train else 1e-5
+    tol = 2e-3 if train else 2e-5
     assert rel(df_o, df_r) < tol and rel(dw_o, dw_r) < tol and rel(dfp_o, dfp_r) < tol, \
         (rel(df_o, df_r), rel(dw_o, dw_r), rel(dfp_o, dfp_r))
