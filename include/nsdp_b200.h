@@ -298,6 +298,15 @@ int nsdp_emlp_bwd_f32(const nsdp_emlp_args *args, const float *t1, const float *
                       const float *d_out, const nsdp_emlp_grads *grads, void *workspace, size_t workspace_bytes,
                       void *stream);
 
+/* Staging format of the operand tiles that the decoder attention / decoder tail backward hand to the weight-gradient
+ * reduction through HBM (the dominant HBM traffic of a training step; csrc/stage_f16.cuh):
+ *   1 = fp16 (default): 2 B / element, one MMA per product, gradient tiles scaled by a power of two derived from a sample
+ *       of max|d_out|; weight / table gradients carry a relative error of ~2e-4 (11-bit operands);
+ *   0 = bf16 hi + lo: 4 B / element, three MMAs per product, fp32-grade (~1e-5) at twice the traffic.
+ * Process-wide; returns the previous format; any other value only queries. Environment override at first use:
+ * NSDP_STAGE_FMT=fp16 | bf16x2. The encoder's attention blocks and nsdp_fused_mlp_bwd_f32 always use bf16 hi + lo. */
+int nsdp_set_stage_format(int fmt);
+
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
  * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.

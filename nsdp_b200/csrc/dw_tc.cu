@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "dw_tc.cuh"
+#include "stage_f16.cuh"
 #include "umma.cuh"
 
 namespace nsdp {
@@ -80,9 +81,10 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
     *reinterpret_cast<uint4 *>(ones + t * 32) = make_uint4(0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4 *>(ones + t * 32 + 16) = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    if (t < 8) {   // rows 2t, 2t+1 of column group 0: element (r, 0) = bf16 1.0
-      *reinterpret_cast<uint32_t *>(ones + t * 32) = 0x00003F80u;
-      *reinterpret_cast<uint32_t *>(ones + t * 32 + 16) = 0x00003F80u;
+    if (t < 8) {   // rows 2t, 2t+1 of column group 0: element (r, 0) = 1.0 (bf16, or fp16 for fp16-staged jobs)
+      const uint32_t one = job.f16 ? 0x00003C00u : 0x00003F80u;
+      *reinterpret_cast<uint32_t *>(ones + t * 32) = one;
+      *reinterpret_cast<uint32_t *>(ones + t * 32 + 16) = one;
     }
     fence_async_smem();
   }
@@ -124,7 +126,8 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
     // MMA issuer: whole warp runs the loop and the waits, one elected lane issues (elect_one: straight UTCHMMA issue);
     // descriptors advance by adds, the ring position is a running counter
     if (has_work) {
-      const uint32_t idesc = idesc_bf16_mn(128, job.wy);
+      // kind::f16 instruction descriptor: operand formats in bits [7,10) / [10,13), 1 = bf16, 0 = fp16
+      const uint32_t idesc = job.f16 ? (idesc_bf16_mn(128, job.wy) & ~((1u << 7) | (1u << 10))) : idesc_bf16_mn(128, job.wy);
       const uint64_t x0 = smem_desc(smem_u32(smem), 128, 256);
       const uint64_t ones_desc = smem_desc(smem_u32(ones), 128, 256);
       const uint32_t stage16 = stage_bytes >> 4;
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       // the four warps split the 16 rows of a k-step. All rows -> bias gradients (colsum); a periodic subset of rows
       // (row % g_kr == g_kr - 1, g_kr a power of two) -> per-batch sums (gsum, the decoder's global-token rows).
       const int w4 = warp - 2;
+      const float osc = job.gmax ? 1.f / stage16::scale_from_max(*job.gmax) : 1.f;
       float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int gb = -1;   // batch the running gs[] belongs to
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
         if (gb >= 0 && mine) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (lane * 8 + u < job.nv) atomicAdd(job.gsum + (size_t)gb * job.nv + lane * 8 + u, gs[u]);
+            if (lane * 8 + u < job.nv) atomicAdd(job.gsum + (size_t)gb * job.nv + lane * 8 + u, gs[u] * osc);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) gs[u] = 0.f;
@@ -199,8 +203,14 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
                 float v[8];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  v[2 * u] = __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
-                  v[2 * u + 1] = __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                  if (job.f16) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hw[u]));
+                    v[2 * u] = f.x;
+                    v[2 * u + 1] = f.y;
+                  } else {
+                    v[2 * u] = __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+                    v[2 * u + 1] = __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                  }
                 }
                 if (want_cs) {
 #pragma unroll
@@ -226,10 +236,11 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       if (want_cs && mine) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (lane * 8 + u < job.nv) atomicAdd(job.colsum + lane * 8 + u, cs[u]);
+          if (lane * 8 + u < job.nv) atomicAdd(job.colsum + lane * 8 + u, cs[u] * osc);
       }
     }
     // flush: TMEM lane = output row m, columns = n
+    const float osc = job.gmax ? 1.f / stage16::scale_from_max(*job.gmax) : 1.f;
     const int quarter = warp & 3;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     mbar_wait(&acc_done, 0, p.err);
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
           float *dst = job.out + (size_t)m * job.ldo + n0;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (n0 + u < job.nv) atomicAdd(dst + u, v[u]);
+            if (n0 + u < job.nv) atomicAdd(dst + u, v[u] * osc);
         }
       }
     }
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
         if (lane == 0) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (n0 + u < job.nv) atomicAdd(job.colsum + n0 + u, v[u]);
+            if (n0 + u < job.nv) atomicAdd(job.colsum + n0 + u, v[u] * osc);
         }
       }
     }

@@ -23,6 +23,11 @@ struct Job {
   int x_lo = 1, y_lo = 1;
   // tile range of this job inside the staging buffers (tile index relative to x / y); t1 < 0 = all tiles of the launch
   long long t0 = 0, t1 = -1;
+  // f16 != 0: both operands are staged as ONE fp16 slab per k-step (csrc/stage_f16.cuh; x_lo = y_lo = 0 then) and the
+  // product is a single f16 x f16 MMA. gmax != nullptr: device word holding the float bits of max|g| from which the
+  // producer derived its power-of-two gradient scale; every result of the job is multiplied by its inverse.
+  int f16 = 0;
+  const unsigned *gmax = nullptr;
   // chunked launches only: `out` advances by this many floats per shape index of the CTA's chunk (per-shape outputs)
   long long out_shape_stride = 0;
 };

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "dw_tc.cuh"
+#include "stage_f16.cuh"
 #include "umma.cuh"
 
 namespace nsdp {
@@ -144,6 +145,8 @@ struct Staging {
   unsigned char *dn[MAXB + 1];     // dn[i] = d n_i (i < n), dn[n] = d net_n
   unsigned char *dout;             // width 16
   int lo;                          // 1: [hi slab][lo slab] per k-step (fp32-grade), 0: hi slab only (plain bf16 operand tiles)
+  int f16;                         // 1 (lo == 0): the slab holds fp16 values, gradient tiles scaled by 2^k (stage_f16.cuh)
+  const unsigned *gmax;            // float bits of max|d_out| the scale is derived from
 };
 
 template <int W>
@@ -151,6 +154,12 @@ __device__ __forceinline__ void stage_write(unsigned char *tile, int r, int k0, 
   unsigned char *p = tile + (size_t)(r >> 4) * ((has_lo ? 2 : 1) * W * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
   *reinterpret_cast<uint4 *>(p) = hi;
   if (has_lo) *reinterpret_cast<uint4 *>(p + W * 32) = lo;
+}
+
+template <int W>
+__device__ __forceinline__ void stage_write16(unsigned char *tile, int r, int k0, const float (&x)[8], float sc) {
+  unsigned char *p = tile + (size_t)(r >> 4) * (W * 32) + (size_t)(k0 >> 3) * 256 + (r & 15) * 16;
+  *reinterpret_cast<uint4 *>(p) = stage16::pack8(x, sc);
 }
 
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
@@ -368,7 +377,8 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
       TW(202);
     };
     // v[0..32) of this thread's hidden columns -> X operand (+ optional staged copy)
-    auto put_x = [&](const float (&v)[XPT], unsigned char *stage_tile) {
+    const float gsc = stg.f16 ? stage16::scale_from_max(*stg.gmax) : 1.f;   // gradient tiles are staged times gsc
+    auto put_x = [&](const float (&v)[XPT], unsigned char *stage_tile, float sc = 1.f) {
 #pragma unroll
       for (int j = 0; j < XPT; j += 8) {
         const float x[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
@@ -377,7 +387,10 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
         const uint32_t off = canon_off(128, r, xb + j);
         *reinterpret_cast<uint4 *>(X_hi + off) = hi;
         *reinterpret_cast<uint4 *>(X_lo + off) = lo;
-        if (stage_tile) stage_write<H>(stage_tile, r, xb + j, hi, lo, stg.lo);
+        if (stage_tile) {
+          if (stg.f16) stage_write16<H>(stage_tile, r, xb + j, x, sc);
+          else stage_write<H>(stage_tile, r, xb + j, hi, lo, stg.lo);
+        }
       }
     };
     auto load_acc = [&](uint32_t col, float (&v)[XPT]) {
@@ -411,7 +424,8 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
           const uint32_t off = canon_off(128, r, k0);
           *reinterpret_cast<uint4 *>(L_hi + off) = hi;
           *reinterpret_cast<uint4 *>(L_lo + off) = lo;
-          stage_write<C::CP>(stg.lat + toff_c, r, k0, hi, lo, stg.lo);
+          if (stg.f16) stage_write16<C::CP>(stg.lat + toff_c, r, k0, x, 1.f);
+          else stage_write<C::CP>(stg.lat + toff_c, r, k0, hi, lo, stg.lo);
         }
         if (part == 0) {
           float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -425,10 +439,15 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
           const float x0[8] = {d.x, d.y, d.z, d.w, 0.f, 0.f, 0.f, 0.f}, x1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           uint4 hi, lo;
           unsigned char *dt = stg.dout + (size_t)(tile - tile_begin) * tstride * 16;
-          split8(x0, hi, lo);
-          stage_write<16>(dt, r, 0, hi, lo, stg.lo);
-          split8(x1, hi, lo);
-          stage_write<16>(dt, r, 8, hi, lo, stg.lo);
+          if (stg.f16) {
+            stage_write16<16>(dt, r, 0, x0, gsc);
+            stage_write16<16>(dt, r, 8, x1, gsc);
+          } else {
+            split8(x0, hi, lo);
+            stage_write<16>(dt, r, 0, hi, lo, stg.lo);
+            split8(x1, hi, lo);
+            stage_write<16>(dt, r, 8, hi, lo, stg.lo);
+          }
         }
       }
       publish();
@@ -478,12 +497,16 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
 #pragma unroll
         for (int j = 0; j < XPT; j += 8) {
           const float x[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          stage_write<H>(stg.x[nb] + toff_h, r, xb + j, hi, lo, stg.lo);
+          if (stg.f16) {
+            stage_write16<H>(stg.x[nb] + toff_h, r, xb + j, x, 1.f);
+          } else {
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            stage_write<H>(stg.x[nb] + toff_h, r, xb + j, hi, lo, stg.lo);
+          }
         }
       }
-      put_x(dnet, stg.dn[nb] + toff_h);
+      put_x(dnet, stg.dn[nb] + toff_h, gsc);
       publish();
       // ---- backward through the blocks ---------------------------------------------------------------------------------------------
       for (int i = nb - 1; i >= 0; --i) {
@@ -491,13 +514,13 @@ resnet_tail_bwd_tc_kernel(const nsdp_tail_args a, const float *__restrict__ dout
         load_acc(ACC_H, v);
 #pragma unroll
         for (int j = 0; j < XPT; ++j) v[j] = ((my[i] >> j) & 1u) ? v[j] : 0.f;
-        put_x(v, stg.dhh[i] + toff_h);
+        put_x(v, stg.dhh[i] + toff_h, gsc);
         publish();
         wait_acc();                       // dx
         load_acc(ACC_H, v);
 #pragma unroll
         for (int j = 0; j < XPT; ++j) dnet[j] += ((mx[i] >> j) & 1u) ? v[j] : 0.f;
-        put_x(dnet, stg.dn[i] + toff_h);
+        put_x(dnet, stg.dn[i] + toff_h, gsc);
         publish();
       }
       // ---- d_lat ----------------------------------------------------------------------------------------------------------------------
@@ -556,9 +579,13 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
   // staging precision of the operand tiles of the weight-gradient reductions: fp32-grade (hi + lo) unless
   // NSDP_STAGE_LO=0 opts into plain bf16 tiles (see vattn_bwd_tc.cu: stage_lo_for)
   static const int forced_lo = [] { const char *e = getenv("NSDP_STAGE_LO"); return e ? atoi(e) : 1; }();
-  const int lo = forced_lo != 0;
+  const int f16 = stage16::enabled() ? 1 : 0;
+  const int lo = forced_lo != 0 && !f16;
+  unsigned *gmax = (unsigned *)err + 16;   // inside the 256-byte header
   Staging stg;
   stg.lo = lo;
+  stg.f16 = f16;
+  stg.gmax = gmax;
   {
     unsigned char *p = sbase;
     auto take = [&](int width) { unsigned char *q = p; p += (size_t)seg * (lo ? 512 : 256) * width; return q; };
@@ -569,8 +596,12 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     for (int i = 0; i <= nb; ++i) stg.dn[i] = take(H);
     stg.dout = take(16);
   }
-  cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), st);
+  cudaError_t e = cudaMemsetAsync(err, 0, 256, st);
   if (e != cudaSuccess) return cuda_rc(e);
+  if (f16) {
+    const int r0 = stage16::launch_absmax(dout, (size_t)a.R * a.O, gmax, st);
+    if (r0 != NSDP_OK) return r0;
+  }
   pack_tail_bwd_weights_kernel<C><<<num_pack_matrices<C>(nb), 256, 0, st>>>(a, packed);
   int rc = check_launch();
   if (rc != NSDP_OK) return rc;
@@ -603,7 +634,11 @@ static int launch(const nsdp_tail_args &a, const float *dout, const nsdp_tail_gr
     }
     // init_enc: d pre_0 = d net_0 = dn_0 as well
     jobs[nj++] = {stg.lat, stg.dn[0], g.d_wc_t, C::CP, H, a.C, H, wld, g.d_bc, nullptr, 0, 0, 0};
-    for (int j = 0; j < nj; ++j) jobs[j].x_lo = jobs[j].y_lo = lo;
+    for (int j = 0; j < nj; ++j) {
+      jobs[j].x_lo = jobs[j].y_lo = lo;
+      jobs[j].f16 = f16;
+      jobs[j].gmax = f16 ? gmax : nullptr;
+    }
     // chunk-aligned launch: every job walks the same tile chunks at the same time, so `lat` (six readers), dn_i (two) and
     // x_i / y_i come from HBM once and from L2 for the other readers
     const long long bounds[2] = {0, n};

@@ -16,8 +16,10 @@
 //     d_wg2t += G^T dA,   d_wpt += H^T dGP,   d_wd2t += H^T dS.
 // The op processes the rows in segments so that the staging workspace stays bounded.
 #include <stdlib.h>
+#include <string.h>
 
 #include "dw_tc.cuh"
+#include "stage_f16.cuh"
 #include "vattn_tc_common.cuh"
 
 namespace nsdp {
@@ -602,6 +604,8 @@ static int launch_bwd(const nsdp_vattn_args &a, const float *out, const float *s
 struct OhStaging {
   unsigned char *h, *g, *da, *dgp, *ds, *e;
   int lo;   // 1: [hi slab][lo slab] per k-step, 0: hi slab only
+  int f16;  // 1 (with lo == 0): the single slab holds fp16 values, gradient tiles scaled by 2^k (stage_f16.cuh)
+  const unsigned *gmax;   // float bits of max|d_out| (sampled) the scale is derived from
 };
 
 template <class C>
@@ -805,7 +809,9 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       if (lane == 0) mbar_arrive(a_ready);
     };
     // x[8] -> bf16 hi/lo words; optional A operand store, optional staged store
-    auto emit = [&](const float (&x)[8], int ch, bool to_a, unsigned char *stage_tile, uint4 &hi, uint4 &lo) {
+    // gradient tiles are staged times gsc (a power of two, 1 unless fp16 staging is on)
+    const float gsc = stg.f16 ? stage16::scale_from_max(*stg.gmax) : 1.f;
+    auto emit = [&](const float (&x)[8], int ch, bool to_a, unsigned char *stage_tile, uint4 &hi, uint4 &lo, float sc = 1.f) {
       split2(x[0], x[1], hi.x, lo.x);
       split2(x[2], x[3], hi.y, lo.y);
       split2(x[4], x[5], hi.z, lo.z);
@@ -816,8 +822,12 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       }
       if (stage_tile) {
         unsigned char *p = stage_tile + st_row + (size_t)ch * 256;
-        *reinterpret_cast<uint4 *>(p) = hi;
-        if (stg.lo) *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+        if (stg.f16) {
+          *reinterpret_cast<uint4 *>(p) = stage16::pack8(x, sc);
+        } else {
+          *reinterpret_cast<uint4 *>(p) = hi;
+          if (stg.lo) *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+        }
       }
     };
 
@@ -856,6 +866,12 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
           }
           *reinterpret_cast<uint4 *>(E + a_base + ch * 2048) = e;
+          if (stg.f16) {   // the staged copy feeds an fp16 product: 1.0 = 0x3C00 there (bf16: 0x3F80)
+            e.x = e.x ? (e.x > 0xffffu ? 0x3C000000u : 0x00003C00u) : 0u;
+            e.y = e.y ? (e.y > 0xffffu ? 0x3C000000u : 0x00003C00u) : 0u;
+            e.z = e.z ? (e.z > 0xffffu ? 0x3C000000u : 0x00003C00u) : 0u;
+            e.w = e.w ? (e.w > 0xffffu ? 0x3C000000u : 0x00003C00u) : 0u;
+          }
           *reinterpret_cast<uint4 *>(stg.e + tl * (size_t)(256 * C::E_COLS) + ste_row + (size_t)ch * 256) = e;
         }
       }
@@ -933,8 +949,8 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           }
           if (ch < C::CHUNKS) {
             uint4 hi, lo;
-            emit(da, ch, true, stg.da + tl * st_tile, hi, lo);
-            emit(ds, ch, false, stg.ds + tl * st_tile, hi, lo);
+            emit(da, ch, true, stg.da + tl * st_tile, hi, lo, gsc);
+            emit(ds, ch, false, stg.ds + tl * st_tile, hi, lo, gsc);
             const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
             tmem_st8(trow + C::ACC1_COL + ch * 8, pk);
           }
@@ -968,7 +984,7 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
 #pragma unroll
           for (int j = 0; j < 8; ++j) dg[j] = ((gmaskbits >> (q * 8 + j)) & 1ull) ? dg[j] : 0.f;
           uint4 hi, lo;
-          emit(dg, ch, false, stg.dgp + tl * st_tile, hi, lo);
+          emit(dg, ch, false, stg.dgp + tl * st_tile, hi, lo, gsc);
           const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
           tmem_st8(trow + ch * 8, pk);
         }
@@ -1452,7 +1468,7 @@ __global__ void finalize_tables_kernel(const float *__restrict__ dt1, const floa
 // ~2e-3 relative error on weight gradients whose per-row terms cancel (tools/big_grad_check.py), so it is opt-in.
 static bool stage_lo_for(long long /*pair_rows*/) {
   static const int forced = [] { const char *e = getenv("NSDP_STAGE_LO"); return e ? atoi(e) : 1; }();
-  return forced != 0;
+  return forced != 0 && !stage16::enabled();
 }
 
 static bool no_saved() {
@@ -1488,16 +1504,22 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
   float *dt2 = dt1 + tbl;
   unsigned char *sbase = (unsigned char *)(dt2 + tbl);
   const size_t per = (size_t)seg * slabs * 256 * C::DP;
-  OhStaging stg{sbase, sbase + per, sbase + 2 * per, sbase + 3 * per, sbase + 4 * per, sbase + 5 * per, lo};
+  const int f16 = (!lo && stage16::enabled()) ? 1 : 0;
+  unsigned *gmax = (unsigned *)err + 16;     // inside the zeroed 256-byte header
+  OhStaging stg{sbase, sbase + per, sbase + 2 * per, sbase + 3 * per, sbase + 4 * per, sbase + 5 * per, lo, f16, gmax};
   cudaError_t e = cudaMemsetAsync(err, 0, 256 + 2 * tbl * sizeof(float), st);
   if (e != cudaSuccess) return cuda_rc(e);
+  if (f16) {
+    const int r0 = stage16::launch_absmax(dout, (size_t)a.B * a.M * a.D, gmax, st);
+    if (r0 != NSDP_OK) return r0;
+  }
   pack_bwd_weights_kernel<C><<<96, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
   int rc = check_launch();
   if (rc != NSDP_OK) return rc;
   pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables);
   rc = check_launch();
   if (rc != NSDP_OK) return rc;
-  const bool use_saved = a.saved && a.saved_bytes >= saved_bytes_total<C>(tiles) && !no_saved();
+  const bool use_saved = a.saved && a.saved_bytes >= saved_bytes_total<C>(tiles) && !no_saved() && !f16;
   const unsigned char *saved = (const unsigned char *)a.saved;
   auto kern = vattn_bwd_oh_kernel<C>;
   auto kern_sv = vattn_bwd_sv_kernel<C>;
@@ -1532,6 +1554,7 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
     auto wjob = [&](const unsigned char *x, int xlo, const unsigned char *y, float *o) {
       dwtc::Job j{x, y, o, C::DP, C::DP, a.D, a.D, a.D, nullptr, nullptr, 0, 0, 0};
       j.x_lo = xlo; j.y_lo = lo;
+      j.f16 = f16; j.gmax = f16 ? gmax : nullptr;
       return j;
     };
     // H and G: from this segment's staging, or (saved variant) straight from the forward's buffer, always hi + lo there
@@ -1554,6 +1577,7 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
           dwtc::Job j{stg.e, m == 0 ? stg.dgp : stg.ds, (m == 0 ? dt1 : dt2) + (size_t)b0 * C::E_COLS * a.D, C::E_COLS, C::DP,
                       a.N + 1, a.D, a.D, nullptr, nullptr, 0, 0, 0};
           j.x_lo = 0; j.y_lo = lo; j.out_shape_stride = (long long)C::E_COLS * a.D;
+          j.f16 = f16; j.gmax = f16 ? gmax : nullptr;
           cj[3 + m] = j;
         }
         rc = dw_tc_launch_chunked(cj, 5, n, bounds, ns, err, st);
@@ -1571,6 +1595,7 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
         dwtc::Job j{stg.e, m == 0 ? stg.dgp : stg.ds, (m == 0 ? dt1 : dt2) + (size_t)b * C::E_COLS * a.D, C::E_COLS, C::DP,
                     a.N + 1, a.D, a.D, nullptr, nullptr, 0, 0, 0};
         j.x_lo = 0; j.y_lo = lo; j.t0 = r0; j.t1 = r1;
+        j.f16 = f16; j.gmax = f16 ? gmax : nullptr;
         jobs[nj++] = j;
       }
     }

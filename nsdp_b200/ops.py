@@ -33,6 +33,13 @@ TAIL_IMPL = int(__import__("os").environ.get("NSDP_B200_TAIL_IMPL", "0"))
 # chip is cheaper than a round trip through HBM on this part.
 SAVE_ACTIVATIONS = int(__import__("os").environ.get("NSDP_B200_SAVE_ACTIVATIONS", "0")) != 0
 
+def set_stage_format(fmt: str) -> str:
+    """'fp16' (default) or 'bf16x2': staging format of the decoder backward's weight-gradient operand tiles
+    (nsdp_set_stage_format in include/nsdp_b200.h). Returns the previous format."""
+    code = {"bf16x2": 0, "fp16": 1}[fmt]
+    return ("bf16x2", "fp16")[_lib.lib().nsdp_set_stage_format(code)]
+
+
 TIMING = False     # when True every kernel call below is bracketed by CUDA events on the launching stream
 _TIMED = []        # (name, start_event, end_event)
 

@@ -141,20 +141,32 @@ BWD_CASES = [
 KINK_FREE = {"vp", "vc", "gv", "wd2t", "wg2t"}
 
 
-def _tc_grad_ok(name, got, ref):
+@pytest.fixture(params=["fp16", "bf16x2"])
+def stage_fmt(request):
+    """Both staging formats of the decoder backward's weight-gradient operands (include/nsdp_b200.h: nsdp_set_stage_format)."""
+    prev = ops.set_stage_format(request.param)
+    yield request.param
+    ops.set_stage_format(prev)
+
+
+def _tc_grad_ok(name, got, ref, fmt="bf16x2"):
     """Tolerances for the bf16x3 tensor-core backward. The chain reproduces pre-activations to ~3e-6, which flips the
     ReLU mask of the handful of elements whose pre-activation lies within ~1e-5 of zero (measured on the GPU AND
     reproduced bit-for-bit in magnitude by a CPU emulation of the bf16x3 arithmetic: ~4 flips in 360k elements give
     4e-3 relative L2 on d gp and up to 8e-3 on the gradients that sum it). Those gradients get a bound that only
     catches real bugs (a wrong term is O(1)); everything that does not depend on a mask decision stays at 1e-4."""
     err = _rel_err(got, ref)
-    return err < (1e-4 if name in KINK_FREE else 2e-2), err
+    # fp16-staged operand tiles (11 significant bits) put ~2e-4 on the weight / table gradients (measured 2.1e-4 on d vp)
+    tight = 1e-4 if fmt == "bf16x2" else 5e-4
+    return err < (tight if name in KINK_FREE else 2e-2), err
 
 
 @pytest.mark.parametrize("cfg", BWD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 @pytest.mark.parametrize("sign", [1.0, -1.0])
 @pytest.mark.parametrize("impl", [1, 0], ids=["fp32", "auto"])
-def test_vattn_backward(cfg, sign, impl, monkeypatch):
+def test_vattn_backward(cfg, sign, impl, monkeypatch, stage_fmt):
+    if impl == 1 and stage_fmt != "fp16":
+        pytest.skip("the fp32 CUDA-core kernels stage nothing")
     monkeypatch.setattr(ops, "VATTN_IMPL", impl)
     case = _rel_case = _rand_case(seed=11, **cfg)
     names = [k for k, v in case.items() if torch.is_tensor(v) and v.is_floating_point()]
@@ -172,7 +184,7 @@ def test_vattn_backward(cfg, sign, impl, monkeypatch):
             err = _rel_err(dev[k].grad, cpu[k].grad)
             assert err < 2e-4, (k, err)
         else:           # tensor-core kernels where instantiated (bf16x3)
-            ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad)
+            ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad, stage_fmt)
             assert ok, (k, info)
 
 
@@ -194,7 +206,9 @@ def test_vattn_backward_self_attention_shares_xyz():
 @pytest.mark.parametrize("impl", [1, 0], ids=["fp32", "auto"])
 @pytest.mark.parametrize("R,C,nb,O", [(1000, 200, 5, 3), (64, 200, 5, 3), (1, 200, 5, 3), (333, 256, 2, 1), (130, 64, 1, 4),
                                       (20000, 200, 5, 3)])
-def test_resnet_tail_backward(R, C, nb, O, impl, monkeypatch):
+def test_resnet_tail_backward(R, C, nb, O, impl, monkeypatch, stage_fmt):
+    if impl == 1 and stage_fmt != "fp16":
+        pytest.skip("the fp32 CUDA-core kernels stage nothing")
     monkeypatch.setattr(ops, "TAIL_IMPL", impl)
     g = torch.Generator().manual_seed(R + C)
     r = lambda *s: torch.randn(*s, generator=g)
@@ -212,7 +226,7 @@ def test_resnet_tail_backward(R, C, nb, O, impl, monkeypatch):
         err = _rel_err(d.grad, c.grad)
         # tensor-core path: every gradient of the tail passes through ReLU masks of recomputed activations (see
         # _tc_grad_ok); d_wo / d_bo (i = 7, 8) do not
-        tol = 2e-4 if (impl == 1 or i >= 7) else 2e-2
+        tol = (2e-4 if (impl == 1 or stage_fmt == "bf16x2") else 5e-4) if (impl == 1 or i >= 7) else 2e-2
         assert err < tol, (i, err)
 
 
@@ -236,7 +250,7 @@ def test_vattn_tc_decoder_forward(M, shape_query, monkeypatch):
 
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-activations"])
-def test_vattn_oh_backward_multi_segment(save, monkeypatch):
+def test_vattn_oh_backward_multi_segment(save, monkeypatch, stage_fmt):
     """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 2250 tiles vs
     segments of 4144): the one-hot chain kernel + weight / per-shape table gradient jobs against the fp32 CUDA-core
     backward on the same inputs."""
@@ -252,7 +266,7 @@ def test_vattn_oh_backward_multi_segment(save, monkeypatch):
         ops.vector_attention(sign=1.0, **dev).backward(go)
         grads[impl] = {k: dev[k].grad for k in names}
     for k in names:
-        ok, info = _tc_grad_ok(k, grads[2][k], grads[1][k])
+        ok, info = _tc_grad_ok(k, grads[2][k], grads[1][k], stage_fmt)
         assert ok, (k, info)
 
 
@@ -268,8 +282,10 @@ def test_vattn_tc_stats_feed_backward(monkeypatch):
     got = ops.vector_attention(sign=1.0, **dev)
     want.sum().backward()
     got.sum().backward()
+    fmt = ops.set_stage_format("fp16")
+    ops.set_stage_format(fmt)
     for k in names:
-        ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad)
+        ok, info = _tc_grad_ok(k, dev[k].grad, cpu[k].grad, fmt)
         assert ok, (k, info)
 
 
