@@ -143,9 +143,10 @@ class _GradBuckets:
             if t is not None:
                 t.mul_(1.0 / world)
         late = self.late
-        self.expected = [set(i for i in self.fired_ids if self.bucket_of[i] == b) for b in range(self.nb)] \
-            if (self.expected is None or late) else self.expected
-        self.works, self.late = [], []
+        if self.fired_ids and (self.expected is None or late):
+            self.expected = [set(i for i in self.fired_ids if self.bucket_of[i] == b) for b in range(self.nb)]
+        # ready for the next step even if nobody calls zero() in Python (CUDA-graph replays run no Python in between)
+        self.works, self.late, self.launched, self.fired_ids = [], [], 0, set()
         if late:
             # its in-place accumulation raced with the collective in flight: this step's gradient of that bucket is not
             # trustworthy. Only possible when a parameter that had no gradient on the first step gets one later.
@@ -190,6 +191,11 @@ def sync_training_state(model, optimizer=None) -> None:
                     td.broadcast(t, src=0)
                     if t is not v:
                         v.copy_(t)
+
+
+def set_overlap(model, on: bool) -> None:
+    """Turn the hook-driven early bucket launches off (CUDA-graph capture: a hook would fire only while capturing)."""
+    _buckets_for(model).overlap = bool(on)
 
 
 def zero_grad(model, optimizer) -> None:

@@ -6,12 +6,17 @@ from Python + autograd they leave the GPU idle for milliseconds per step. All sh
 nsdp_b200 kernel is launched on the current stream through the C ABI — so the WHOLE step (forward, loss, backward, fused
 Adam) is captured once into a CUDA graph and replayed: one launch per step.
 
-    step = graphed_train_step(model, optimizer, data_dict, eager_fn)      # -> float loss, same as eager_fn(...)
+    loss = graphed_train_step(model, optimizer, data_dict, forward_backward, finish)     # -> float
+
+`forward_backward(model, optimizer, data_dict) -> loss tensor` is zero_grad + forward + loss + backward;
+`finish(model, optimizer)` is the gradient all-reduce (a no-op on one GPU) + optimizer.step(). On one GPU both are captured
+into ONE graph. Under data parallelism the graph holds forward_backward only — the gradients land in the flat bucket
+buffer of nsdp_b200.dist — and `finish` runs eagerly after the replay (one NCCL all-reduce + the fused Adam kernels).
 
 Protocol per (model, optimizer, input shapes): the first WARMUP calls run eagerly on a side stream (lazy initialisation:
 cuBLAS handles, kernel attributes, gradient buffers, Adam state), the next call captures, later calls copy the batch into
 the graph's static input buffers and replay. Anything that prevents capture (non-capturable optimizer, a failed capture,
-a process group: NCCL calls from autograd hooks are not captured) falls back to the eager path, loudly, once.
+...) falls back to the eager path, loudly, once.
 The learning rate is read from the param groups on every call; a change (model/learningrate.py adjust_learning_rate,
 train.py:188) re-captures, because a Python float lr is baked into the captured launch.
 NSDP_B200_GRAPH=0 disables the whole mechanism.
@@ -65,16 +70,21 @@ def _usable(model, optimizer, data_dict) -> bool:
     if not ENABLED or ops.TIMING:
         return False
     from nsdp_b200 import dist
-    if dist.is_active():
-        return False
-    if not _capturable(optimizer):
+    if not dist.is_active() and not _capturable(optimizer):
         return False
     tensors = [v for v in data_dict.values() if torch.is_tensor(v)]
     return bool(tensors) and all(v.is_cuda for v in tensors) and not torch.cuda.is_current_stream_capturing()
 
 
-def graphed_train_step(model, optimizer, data_dict, eager_fn):
-    """eager_fn(model, optimizer, data_dict) -> loss TENSOR (zero_grad + forward + loss + backward + step, no .item())."""
+def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
+    from nsdp_b200 import dist
+    split = dist.is_active()          # data parallel: the collective and the optimizer stay outside the graph
+
+    def eager_fn(model, optimizer, data_dict):
+        loss = forward_backward(model, optimizer, data_dict)
+        finish(model, optimizer)
+        return loss
+
     if not _usable(model, optimizer, data_dict):
         return eager_fn(model, optimizer, data_dict).item()
     per_model = _STATE.setdefault(model, {})
@@ -97,7 +107,11 @@ def graphed_train_step(model, optimizer, data_dict, eager_fn):
             torch.cuda.current_stream().wait_stream(side)
             return loss.item()
         try:
-            _capture(e, model, optimizer, data_dict, eager_fn)
+            if split:
+                dist.set_overlap(model, False)       # no collectives from autograd hooks while capturing / replaying
+                _capture(e, model, optimizer, data_dict, forward_backward)
+            else:
+                _capture(e, model, optimizer, data_dict, eager_fn)
             e.lrs = lrs
         except Exception as exc:   # noqa: BLE001 — never lose a training step over an optimisation
             e.failed = True
@@ -112,14 +126,19 @@ def graphed_train_step(model, optimizer, data_dict, eager_fn):
             buf.copy_(src, non_blocking=True)
     e.graph.replay()
     ops._count(e.launches)
+    if split:
+        finish(model, optimizer)
     return e.loss.item()
 
 
 def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
     static = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
     passthrough = {k: v for k, v in data_dict.items() if not torch.is_tensor(v)}
-    # gradients must be (re)created INSIDE the capture so that they live in the graph's memory pool
-    optimizer.zero_grad(set_to_none=True)
+    # gradients must be (re)created INSIDE the capture so that they live in the graph's memory pool (single GPU); under
+    # data parallelism they are views of the flat bucket buffer, which exists since the first warm-up step
+    from nsdp_b200 import dist
+    if not dist.is_active():
+        optimizer.zero_grad(set_to_none=True)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     before = ops.LAUNCHES

@@ -50,15 +50,18 @@ def _train_step_with_cano(model, optimizer, data_dict):
     pred = model(data_dict["space_samples_src"], data_dict["surface_samples_inputs"])
     loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
     loss.backward()
+    return loss
+
+
+def _finish_step(model, optimizer):
     nsdp_dist.allreduce_gradients(model)
     optimizer.step()
-    return loss
 
 
 def train_on_batch_with_cano(model, optimizer, data_dict, config):
     """deformation_networks.py:63-77. The step itself is `_train_step_with_cano`; on a GPU it is captured into a CUDA graph
     after a few calls and replayed (nsdp_b200/graph.py) — same arithmetic, one launch per step."""
-    return graphed_train_step(model, optimizer, data_dict, _train_step_with_cano)
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_cano, _finish_step)
 
 
 @torch.no_grad()

@@ -70,14 +70,17 @@ def _train_step_with_arbitrary(model, optimizer, data_dict):
     pred = model(data_dict["space_samples_src"], src, tgt, mask)
     loss = compute_l2_error(pred, data_dict["space_samples_tgt"])
     loss.backward()
+    return loss
+
+
+def _finish_step(model, optimizer):
     nsdp_dist.allreduce_gradients(model)
     optimizer.step()
-    return loss
 
 
 def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
     """flow_arbitrary.py:30-48; captured into a CUDA graph after a few calls (nsdp_b200/graph.py)."""
-    return graphed_train_step(model, optimizer, data_dict, _train_step_with_arbitrary)
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_arbitrary, _finish_step)
 
 
 @torch.no_grad()
