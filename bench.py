@@ -419,6 +419,9 @@ def run_ours(args):
         from nsdp_b200 import graph
         st = [e for per in graph._STATE.values() for e in per.values()]
         if any(e.graph is not None for e in st):
+            if world > 1:
+                return ("forward + backward replayed as ONE CUDA graph, then one NCCL all-reduce of the flat gradient buffer and the "
+                        "fused Adam (a second graph); gpu_launches = kernel calls inside the graph")
             return "whole step (fwd + bwd + Adam) replayed as ONE CUDA graph; gpu_launches = kernel calls inside it"
         return "eager launches" + (" (graph capture failed, see stderr)" if any(e.failed for e in st) else "")
 

@@ -22,6 +22,11 @@
 //   * no eligible point at all -> index 0 (threads contribute (-1, 0) in the reference).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+
+#ifndef NSDP_FPS_VARIANT_DEFAULT
+#define NSDP_FPS_VARIANT_DEFAULT 0
+#endif
 
 #include "common.cuh"
 
@@ -205,7 +210,19 @@ extern "C" int nsdp_fps_f32(const float *xyz, int B, int N, int m, int32_t *out_
   if (N <= 512) return launch_fps<4, 128>(xyz, B, N, m, lb, 1, out_idx, st);
   if (N <= 1024) return launch_fps<2, 512>(xyz, B, N, m, lb, 1, out_idx, st);
   if (N <= 2048) return launch_fps<4, 512>(xyz, B, N, m, lb, 1, out_idx, st);
-  if (N <= 4096) return launch_fps<8, 512>(xyz, B, N, m, lb, 1, out_idx, st);
+  if (N <= 4096) {
+    // per-iteration cost at this size is synchronisation latency, not arithmetic: fewer, fatter warps win (A/B on B200,
+    // tools/microbench_fps.py; NSDP_FPS_VARIANT picks the others)
+    static const int variant = [] { const char *e = getenv("NSDP_FPS_VARIANT"); return e ? atoi(e) : NSDP_FPS_VARIANT_DEFAULT; }();
+    switch (variant) {
+      case 1: return launch_fps<16, 256>(xyz, B, N, m, lb, 1, out_idx, st);
+      case 2: return launch_fps<32, 128>(xyz, B, N, m, lb, 1, out_idx, st);
+      case 3: return launch_fps<4, 512>(xyz, B, N, m, lb, 2, out_idx, st);
+      case 4: return launch_fps<2, 512>(xyz, B, N, m, lb, 4, out_idx, st);
+      case 5: return launch_fps<8, 128>(xyz, B, N, m, lb, 4, out_idx, st);
+      default: return launch_fps<8, 512>(xyz, B, N, m, lb, 1, out_idx, st);
+    }
+  }
   if (N <= 8192) return launch_fps<16, 512>(xyz, B, N, m, lb, 1, out_idx, st);
   int C = 2;
   while (C < kFpsMaxCluster && (long long)C * 8192 < N) C *= 2;

@@ -134,6 +134,13 @@ class _GradBuckets:
             self.launched += 1
 
     def finish(self) -> None:
+        if self.launched == 0 and not self.overlap:
+            # nothing left during backward (CUDA-graph replay, or overlap switched off): ONE collective over the whole buffer
+            if self.avg:
+                self.works.append((td.all_reduce(self.flat, op=td.ReduceOp.AVG, async_op=True), None))
+            else:
+                self.works.append((td.all_reduce(self.flat, op=td.ReduceOp.SUM, async_op=True), self.flat))
+            self.launched = self.nb
         while self.launched < self.nb:
             self._launch(self.launched)
             self.launched += 1

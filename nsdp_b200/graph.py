@@ -37,11 +37,11 @@ _STATE = weakref.WeakKeyDictionary()      # model -> {signature: _Entry}
 
 
 class _Entry:
-    __slots__ = ("calls", "graph", "static", "loss", "lrs", "launches", "failed", "opt_ref")
+    __slots__ = ("calls", "graph", "static", "loss", "lrs", "launches", "failed", "opt_graph")
 
     def __init__(self):
         self.calls, self.graph, self.static, self.loss = 0, None, None, None
-        self.lrs, self.launches, self.failed, self.opt_ref = None, 0, False, None
+        self.lrs, self.launches, self.failed, self.opt_graph = None, 0, False, None
 
 
 def _signature(model, optimizer, data_dict):
@@ -96,7 +96,7 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
         return eager_fn(model, optimizer, data_dict).item()
     lrs = _lrs(optimizer)
     if e.graph is not None and e.lrs != lrs:
-        e.graph, e.static, e.loss = None, None, None           # learning rate changed: capture again
+        e.graph, e.static, e.loss, e.opt_graph = None, None, None, None           # learning rate changed: capture again
     if e.graph is None:
         if e.calls < WARMUP:
             e.calls += 1
@@ -110,6 +110,11 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
             if split:
                 dist.set_overlap(model, False)       # no collectives from autograd hooks while capturing / replaying
                 _capture(e, model, optimizer, data_dict, forward_backward)
+                if _capturable(optimizer):           # the fused Adam launches as a second, tiny graph after the collective
+                    og = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(og):
+                        optimizer.step()
+                    e.opt_graph = og
             else:
                 _capture(e, model, optimizer, data_dict, eager_fn)
             e.lrs = lrs
@@ -127,7 +132,11 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
     e.graph.replay()
     ops._count(e.launches)
     if split:
-        finish(model, optimizer)
+        if e.opt_graph is not None:
+            dist.allreduce_gradients(model)
+            e.opt_graph.replay()
+        else:
+            finish(model, optimizer)
     return e.loss.item()
 
 
