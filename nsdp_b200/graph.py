@@ -161,3 +161,53 @@ def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
     e.launches = ops.LAUNCHES - before
     e.graph, e.static, e.loss = g, static, loss
     # the capture itself executed nothing: the caller replays right away with the current batch
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# inference: eval-mode forward under no_grad (validate_on_batch, test.py / run.py on fixed-size inputs, bench --forward-only)
+# ---------------------------------------------------------------------------------------------------------------------
+_FWD_STATE = weakref.WeakKeyDictionary()      # model -> {signature: _Entry}
+MAX_FORWARD_GRAPHS = 4                        # per model: meshes of many different sizes (test.py) simply stay eager
+
+
+def graphed_forward(model, inputs, eager_fn):
+    """eager_fn(*inputs) -> tensor, for a model in eval mode with gradients disabled: no side effects, so after WARMUP eager
+    calls per input-shape signature the forward is captured and replayed (the result is copied out of the graph's static
+    output buffer). Everything else runs eager_fn directly."""
+    if (not ENABLED or ops.TIMING or model.training or torch.is_grad_enabled() or torch.cuda.is_current_stream_capturing()
+            or not all(torch.is_tensor(t) and t.is_cuda for t in inputs)):
+        return eager_fn(*inputs)
+    per_model = _FWD_STATE.setdefault(model, {})
+    sig = tuple((tuple(t.shape), t.dtype, str(t.device)) for t in inputs)
+    e = per_model.get(sig)
+    if e is None:
+        if len(per_model) >= MAX_FORWARD_GRAPHS:
+            return eager_fn(*inputs)
+        e = per_model[sig] = _Entry()
+    if e.failed:
+        return eager_fn(*inputs)
+    if e.graph is None:
+        if e.calls < WARMUP:
+            e.calls += 1
+            return eager_fn(*inputs)
+        try:
+            static = [t.clone() for t in inputs]
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = eager_fn(*static)
+            e.launches = ops.LAUNCHES - before
+            e.graph, e.static, e.loss = graph, static, out
+        except Exception as exc:   # noqa: BLE001
+            e.failed, e.graph = True, None
+            torch.cuda.synchronize()
+            print(f"[nsdp_b200.graph] CUDA-graph capture of the eval forward failed ({type(exc).__name__}: {exc}); "
+                  "continuing on the eager path", file=sys.stderr)
+            return eager_fn(*inputs)
+    for buf, src in zip(e.static, inputs):
+        if src.data_ptr() != buf.data_ptr():
+            buf.copy_(src, non_blocking=True)
+    e.graph.replay()
+    ops._count(e.launches)
+    return e.loss.clone()

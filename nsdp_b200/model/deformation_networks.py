@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from nsdp_b200 import dist as nsdp_dist
-from nsdp_b200.graph import graphed_train_step
+from nsdp_b200.graph import graphed_forward, graphed_train_step
 from nsdp_b200.model.decoder import decoder_dict
 from nsdp_b200.model.encoder import encoder_dict
 from nsdp_b200.model.utils import compute_l2_error
@@ -41,8 +41,12 @@ class Deformation_Networks(nn.Module):
     def decode(self, points, encoding):
         return self.decoder(points, encoding)
 
-    def forward(self, points, surface_samples_inputs):
+    def _forward(self, points, surface_samples_inputs):
         return self.decode(points, self.encode(surface_samples_inputs))
+
+    def forward(self, points, surface_samples_inputs):
+        # eval mode + no_grad + CUDA inputs of a shape seen before: replayed as one CUDA graph (nsdp_b200/graph.py)
+        return graphed_forward(self, (points, surface_samples_inputs), self._forward)
 
 
 def _train_step_with_cano(model, optimizer, data_dict):
