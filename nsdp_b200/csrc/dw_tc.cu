@@ -35,6 +35,10 @@ struct Params {
   int chunk_t0[MAX_CHUNKS + 1];
   int chunk_shape[MAX_CHUNKS];
   int stages;              // ring depth (<= MAX_STAGES)
+  int group;               // k-steps (of 16 rows) per ring stage: 1, 2, 4 or 8. > 1 only when every job streams exactly what
+                           // is staged (no skipped lo slabs), so that consecutive k-steps of a tile are contiguous in memory:
+                           // fewer, larger bulk copies and barrier round trips per byte (fp16 staging halved the bytes per
+                           // k-step and left the reduction issue-bound at 48 % of the HBM rate; measured, profiles/)
   uint32_t ones_off;       // offset of the constant one-hot operand (column sums by MMA) inside dynamic shared memory
   int terms;               // 3: xh*yh + xl*yh + xh*yl (fp32-grade) ; 2: xh*yh + xl*yh ; 1: xh*yh (plain bf16 operands)
   int *err;
@@ -68,7 +72,8 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
   const uint32_t xk = job.x_lo ? 2 * xs : xs, yk = job.y_lo ? 2 * ys : ys;   // k-step pitch inside a staged tile
   const bool x_lo = job.x_lo && p.terms >= 2, y_lo = job.y_lo && p.terms >= 3;   // which lo slabs are streamed at all
   const uint32_t xb = x_lo ? 2 * xs : xs, yb = y_lo ? 2 * ys : ys;
-  const uint32_t stage_bytes = xb + yb;
+  const int G = p.group;
+  const uint32_t stage_bytes = (uint32_t)G * (xb + yb);   // one ring stage: G k-steps of X, then G k-steps of Y
   const int mtiles = job.wx > 128 ? 2 : 1;
   // Column sums (bias gradients) by the tensor core: colsum[n] = sum_r ONES[r][0] * Y[r][n] with the constant operand
   // ONES[r][m] = (m == 0), accumulated in a spare TMEM region whose row 0 is flushed at the end. The warp-level path
@@ -109,17 +114,19 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
     // one copy per ~500 cycles: the wait / expect_tx / issue chain is serial; measured with tools/micro/stream_bw.cu)
     const int PL = STAGES >= 4 ? STAGES / 2 : 1;
     if (lane < PL) {
-      const long long total = (t1 - t0) * 8;
+      const int spt = 8 / G;                      // stages per tile
+      const long long total = (t1 - t0) * spt;
       for (long long it = lane; it < total; it += PL) {
-        const long long t = t0 + (it >> 3);
-        const int ks = (int)(it & 7);
+        const long long t = t0 + it / spt;
+        const int ks = (int)(it % spt) * G;       // first k-step of the stage
         const int s = (int)(it % STAGES);
         const uint32_t ph = (uint32_t)(it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1, p.err);
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         unsigned char *dst = smem + (size_t)s * stage_bytes;
-        bulk_g2s(dst, job.x + (size_t)t * 8 * xk + (size_t)ks * xk, xb, &full[s]);
-        bulk_g2s(dst + xb, job.y + (size_t)t * 8 * yk + (size_t)ks * yk, yb, &full[s]);
+        // G > 1 implies xk == xb and yk == yb: the G k-steps are one contiguous run
+        bulk_g2s(dst, job.x + (size_t)t * 8 * xk + (size_t)ks * xk, (uint32_t)G * xb, &full[s]);
+        bulk_g2s(dst + (size_t)G * xb, job.y + (size_t)t * 8 * yk + (size_t)ks * yk, (uint32_t)G * yb, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -133,24 +140,27 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       const uint32_t stage16 = stage_bytes >> 4;
       uint32_t slot = 0, slot_phase = 0;
       bool first = true;
-      const long long total = (t1 - t0) * 8;
+      const long long total = (t1 - t0) * (8 / G);
       for (long long it = 0; it < total; ++it) {
         mbar_wait(&full[slot], slot_phase, p.err);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t xh0 = x0 + (uint64_t)slot * stage16;
-          const uint64_t yh = xh0 + (xb >> 4), yl = yh + (ys >> 4);
-          for (int j = 0; j < mtiles; ++j) {
-            // M-tile j = output rows [128j, 128j+128) = column groups 16j.. of the X slab (4096 bytes further)
-            const uint64_t xh = xh0 + (uint64_t)j * (4096 >> 4), xl = xh + (xs >> 4);
-            const uint32_t d = tmem_base + j * 256;
-            mma_bf16(d, xh, yh, idesc, !first);
-            if (x_lo) mma_bf16(d, xl, yh, idesc, true);
-            if (y_lo) mma_bf16(d, xh, yl, idesc, true);
-          }
-          if (mma_cs) {
-            mma_bf16(tmem_base + cs_col, ones_desc, yh, idesc, !first);
-            if (y_lo) mma_bf16(tmem_base + cs_col, ones_desc, yl, idesc, true);
+          for (int gk = 0; gk < G; ++gk) {
+            const uint64_t xh0 = x0 + (uint64_t)slot * stage16 + (uint64_t)gk * (xb >> 4);
+            const uint64_t yh = x0 + (uint64_t)slot * stage16 + (uint64_t)G * (xb >> 4) + (uint64_t)gk * (yb >> 4), yl = yh + (ys >> 4);
+            const bool acc = !first || gk > 0;
+            for (int j = 0; j < mtiles; ++j) {
+              // M-tile j = output rows [128j, 128j+128) = column groups 16j.. of the X slab (4096 bytes further)
+              const uint64_t xh = xh0 + (uint64_t)j * (4096 >> 4), xl = xh + (xs >> 4);
+              const uint32_t d = tmem_base + j * 256;
+              mma_bf16(d, xh, yh, idesc, acc);
+              if (x_lo) mma_bf16(d, xl, yh, idesc, true);
+              if (y_lo) mma_bf16(d, xh, yl, idesc, true);
+            }
+            if (mma_cs) {
+              mma_bf16(tmem_base + cs_col, ones_desc, yh, idesc, acc);
+              if (y_lo) mma_bf16(tmem_base + cs_col, ones_desc, yl, idesc, true);
+            }
           }
           mma_commit(&empty[slot]);
         }
@@ -184,12 +194,14 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       };
       uint32_t it = 0;
       for (long long t = t0; t < t1; ++t) {
-        for (int ks = 0; ks < 8; ++ks, ++it) {
+        for (int ks0 = 0; ks0 < 8; ks0 += G, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph, p.err);
+          for (int gk = 0; gk < G; ++gk) {
+          const int ks = ks0 + gk;
           if ((want_cs || want_gs) && mine) {
-            const unsigned char *yh = smem + (size_t)s * stage_bytes + xb + (size_t)lane * 256;
+            const unsigned char *yh = smem + (size_t)s * stage_bytes + (size_t)G * xb + (size_t)gk * yb + (size_t)lane * 256;
             const unsigned char *yl = yh + ys;
             const unsigned row0 = (unsigned)(t * 128) + (unsigned)(ks * 16);   // row inside the segment (< 2^31)
 #pragma unroll
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
                 }
               }
             }
+          }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);
@@ -287,6 +300,29 @@ static int dw_terms() {
   return t;
 }
 
+// dynamic shared memory the kernel may use: 227 KB minus its static part (barriers) with some slack. The function attribute
+// is raised to this ONCE: a per-launch value would be baked differently into every captured graph node (and a profiler that
+// replays single nodes then launches them with whatever value was set last).
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;
+static int set_smem_limit() {
+  static const cudaError_t e =
+      cudaFuncSetAttribute(dwtc::dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+  return e == cudaSuccess ? NSDP_OK : cuda_rc(e);
+}
+
+// k-steps per ring stage (Params::group)
+static int pick_group(const dwtc::Job *jobs, int njobs, int terms, size_t max_stage) {
+  static const int forced = [] { const char *e = getenv("NSDP_DW_GROUP"); return e ? atoi(e) : 0; }();
+  for (int i = 0; i < njobs; ++i) {
+    const bool x_streamed_lo = jobs[i].x_lo && terms >= 2, y_streamed_lo = jobs[i].y_lo && terms >= 3;
+    if ((jobs[i].x_lo && !x_streamed_lo) || (jobs[i].y_lo && !y_streamed_lo)) return 1;   // pitch != streamed bytes
+  }
+  int g = 1;
+  while (g < 8 && (size_t)(2 * g) * max_stage * 4 <= kSmemBudget - 2 * 4096) g *= 2;       // keep >= 4 stages in flight
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) g = forced < g ? forced : g;
+  return g;
+}
+
 // Launches the reduction for `njobs` jobs that all span `tiles` row tiles.
 int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cudaStream_t st) {
   using namespace dwtc;
@@ -309,6 +345,7 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   }
   p.njobs = njobs;
   p.nchunks = 0;
+  p.group = pick_group(p.jobs, njobs, p.terms, max_stage);
   // CTAs per job: proportional to bytes, at least 1, at most the job's tile count; about one CTA per SM in total
   const int budget = num_sms() > njobs ? num_sms() : njobs;
   int ctas = 0;
@@ -324,7 +361,8 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   p.err = err;
   // The ring is as deep as shared memory allows (+ slack for the M-tile-1 overrun): the operand tiles stream from HBM
   // (several microseconds of latency under load), 4 stages left the SMs waiting
-  int stages = (int)((227 * 1024 - 2 * 4096 - 1024) / max_stage);
+  max_stage *= (size_t)p.group;
+  int stages = (int)((kSmemBudget - 2 * 4096) / max_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return NSDP_ERR_UNSUPPORTED;
   static const int forced = [] { const char *e = getenv("NSDP_DW_STAGES"); return e ? atoi(e) : 0; }();
@@ -332,8 +370,8 @@ int dw_tc_launch(const dwtc::Job *jobs, int njobs, long long tiles, int *err, cu
   p.stages = stages;
   p.ones_off = (uint32_t)((size_t)stages * max_stage + 4096);
   const size_t smem = (size_t)stages * max_stage + 2 * 4096;
-  cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_rc(e);
+  const int rc0 = set_smem_limit();
+  if (rc0 != NSDP_OK) return rc0;
   dw_tc_kernel<<<ctas, THREADS, smem, st>>>(p);
   return check_launch();
 }
@@ -356,6 +394,7 @@ int dw_tc_launch_chunked(const dwtc::Job *jobs, int njobs, long long tiles, cons
     max_stage = stage > max_stage ? stage : max_stage;
   }
   p.njobs = njobs;
+  p.group = pick_group(p.jobs, njobs, p.terms, max_stage);
   // about one CTA per SM in total: P chunks, dealt out to the shapes by length (at least one each), uniform inside a shape
   int P = num_sms() / njobs;
   if (P < nshapes) P = nshapes;
@@ -378,14 +417,15 @@ int dw_tc_launch_chunked(const dwtc::Job *jobs, int njobs, long long tiles, cons
   }
   p.nchunks = nc;
   p.err = err;
-  int stages = (int)((227 * 1024 - 2 * 4096 - 1024) / max_stage);
+  max_stage *= (size_t)p.group;
+  int stages = (int)((kSmemBudget - 2 * 4096) / max_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return NSDP_ERR_UNSUPPORTED;
   p.stages = stages;
   p.ones_off = (uint32_t)((size_t)stages * max_stage + 4096);
   const size_t smem = (size_t)stages * max_stage + 2 * 4096;
-  cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_rc(e);
+  const int rc0 = set_smem_limit();
+  if (rc0 != NSDP_OK) return rc0;
   dw_tc_kernel<<<nc * njobs, THREADS, smem, st>>>(p);
   return check_launch();
 }
