@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
     fence_async_smem();
   }
 
+  // the four flush warps also read the slabs in the ring only for warp-level column sums (bias gradients without a spare
+  // TMEM region, per-batch sums); otherwise they stay out of the ring protocol altogether
+  const bool ring_warps = (job.colsum != nullptr && !mma_cs) || job.gsum != nullptr;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 5);  // MMA commit + the four column-sum warps
+      mbar_init(&empty[s], ring_warps ? 5 : 1);  // MMA commit (+ the four column-sum warps)
     }
     mbar_init(&acc_done, 1);
     mbar_fence_init();
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tc_kernel(const Params p) {
       if (elect_one()) mma_commit(&acc_done);
     }
   } else if (has_work) {
-    {
+    if (ring_warps) {
       // Column sums of Y straight from the staged slabs as they pass through shared memory. Lane = column group of 8;
       // the four warps split the 16 rows of a k-step. All rows -> bias gradients (colsum); a periodic subset of rows
       // (row % g_kr == g_kr - 1, g_kr a power of two) -> per-batch sums (gsum, the decoder's global-token rows).

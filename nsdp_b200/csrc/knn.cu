@@ -14,6 +14,8 @@
 // the stable order torch's unstable argsort leaves undefined on ties. Index tensors are int32.
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nsdp {
@@ -132,6 +134,8 @@ __global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t
 }
 
 static int knn_splits(int B, int M, int N) {
+  static const int forced = [] { const char *e = getenv("NSDP_KNN_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced >= 1 && forced <= 64 && N / forced >= 64) return forced;
   const long long queries = (long long)B * M;
   const long long want = 148ll * 1024;  // ~8 warps per SMSP of scanning threads
   long long S = (want + queries - 1) / queries;

@@ -159,6 +159,7 @@ def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
     with torch.cuda.graph(g):
         loss = eager_fn(model, optimizer, {**static, **passthrough})
     e.launches = ops.LAUNCHES - before
+    ops.LAUNCHES = before            # the capture pass executed nothing; replays account for their kernel calls
     e.graph, e.static, e.loss = g, static, loss
     # the capture itself executed nothing: the caller replays right away with the current batch
 
@@ -198,6 +199,7 @@ def graphed_forward(model, inputs, eager_fn):
             with torch.cuda.graph(graph):
                 out = eager_fn(*static)
             e.launches = ops.LAUNCHES - before
+            ops.LAUNCHES = before
             e.graph, e.static, e.loss = graph, static, out
         except Exception as exc:   # noqa: BLE001
             e.failed, e.graph = True, None
