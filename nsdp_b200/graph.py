@@ -72,6 +72,8 @@ def _usable(model, optimizer, data_dict) -> bool:
     from nsdp_b200 import dist
     if not dist.is_active() and not _capturable(optimizer):
         return False
+    if dist.is_active() and any(isinstance(m, dist.SyncBatchNorm1d) for m in model.modules()):
+        return False          # syncbn mode issues collectives inside forward / backward: stays eager
     tensors = [v for v in data_dict.values() if torch.is_tensor(v)]
     return bool(tensors) and all(v.is_cuda for v in tensors) and not torch.cuda.is_current_stream_capturing()
 

@@ -1,0 +1,134 @@
+"""Paths that need real GPUs beyond the single-device parity tests:
+  * arbitrary-mode inference encodes each distinct encoder input once and still returns what the
+    reference's two model(...) calls return;
+  * 2 ranks over NCCL (skipped on a 1-GPU box; run with `gpurun --gpus 2`): query-sharded decode, and data-parallel
+    training through train_on_batch (flat gradient buckets, NCCL AVG all-reduce, CUDA-graph replay) against a single
+    process on the whole batch — in syncbn mode, where the two are the same computation."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from nsdp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_arbitrary_inference_encodes_once_and_matches_the_two_call_form(schemas):
+    from nsdp_b200 import ops
+    from nsdp_b200.model import build_model
+    cfg = synth.make_config("arbitrary")
+    model, _, _, test_on_batch = build_model(cfg, device=DEV)
+    model.load_state_dict(synth.named_state_dict([(k, s) for k, s in schemas["arbitrary"]], seed=0))
+    model.eval()
+    b = synth.forward_batch(1, 900, 700, seed=3, fp16_grid=False)
+    surf = b["surface_samples_inputs"].to(DEV)
+    verts = b["space_samples_src"].to(DEV)
+    src, tgt, mask = surf[:, :, 0:3], surf[:, :, 3:6], surf[:, :, 6:7]
+    with torch.no_grad():
+        want_surf = model(src, src, tgt, mask)          # flow_arbitrary.py:71-79: two full passes
+        want_verts = model(verts, src, tgt, mask)
+    data = {"surface_samples_inputs": surf, "verts_src": verts, "verts_tgt": b["space_samples_tgt"].to(DEV)}
+    fps_before = ops.LAUNCHES
+    calls = {"n": 0}
+    orig = ops.furthest_point_sampling
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    ops.furthest_point_sampling = counting
+    try:
+        loss, out = test_on_batch(model, data, cfg, compute_loss=True)
+    finally:
+        ops.furthest_point_sampling = orig
+    assert calls["n"] == 4                                # 2 encoder passes x 2 FPS levels (the reference runs 6 passes)
+    assert float((out["surface_samples_tgt_pred"] - want_surf).norm(dim=-1).mean()) < 1e-6
+    assert float((out["verts_tgt_pred"] - want_verts).norm(dim=-1).mean()) < 1e-6
+    assert np.isfinite(loss) and ops.LAUNCHES > fps_before
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), NSDP_B200_SYNCBN="1")
+    import json
+    import torch.distributed as td
+    from nsdp_b200 import dist as nd
+    from nsdp_b200.model import build_model, optimizer_factory
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "state_dict_schema.json")) as f:
+        schema = json.load(f)["forward"]
+    cfg = synth.make_config("forward")
+    model, train_on_batch, _, _ = build_model(cfg, device=dev)       # joins the NCCL job, converts to syncbn
+    assert td.is_initialized() and td.get_world_size() == world
+    model.load_state_dict(synth.named_state_dict([(k, s) for k, s in schema], seed=0))
+    # ---- query-sharded decode ----
+    model.eval()
+    b = {k: v.to(dev) for k, v in synth.forward_batch(2, 700, 1001, seed=8, fp16_grid=False).items()}
+    with torch.no_grad():
+        enc = model.encode(b["surface_samples_inputs"])
+        whole = model.decode(b["space_samples_src"], enc)
+        seen = []
+
+        def dec(p):
+            seen.append(p.shape[1])
+            return model.decode(p, enc)
+        sharded = nd.sharded_decode(dec, b["space_samples_src"])
+    shard_err = float((sharded - whole).norm(dim=-1).mean())
+    # ---- data-parallel training, 4 steps, global batch 4 ----
+    model.train()
+    _, opt = optimizer_factory(cfg["training"], model.parameters())
+    full = synth.forward_batch(4, 600, 500, seed=21, fp16_grid=False)
+    losses = []
+    for step in range(4):
+        mine = {k: v.to(dev) for k, v in nd.shard_batch(full).items()}
+        losses.append(train_on_batch(model, opt, mine, cfg))
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    q.put((rank, shard_err, seen, losses, sd))
+    td.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_sharded_decode_and_data_parallel_training(schemas):
+    import torch.multiprocessing as mp
+    from nsdp_b200.model import build_model, optimizer_factory
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, shard_err, seen, losses, sd in res:
+        assert shard_err < 1e-6 and seen == [501]             # each rank decoded its (padded) half of the 1001 queries
+    # single process, whole batch of 4, ordinary BatchNorm == 2 ranks x 2 shapes with syncbn
+    cfg = synth.make_config("forward")
+    os.environ["NSDP_B200_DP"] = "0"
+    model, train_on_batch, _, _ = build_model(cfg, device=DEV)
+    model.load_state_dict(synth.named_state_dict([(k, s) for k, s in schemas["forward"]], seed=0))
+    model.train()
+    _, opt = optimizer_factory(cfg["training"], model.parameters())
+    full = {k: v.to(DEV) for k, v in synth.forward_batch(4, 600, 500, seed=21, fp16_grid=False).items()}
+    want = [train_on_batch(model, opt, dict(full), cfg) for _ in range(4)]
+    # per-rank losses are means over the rank's 2 shapes: their average is the global loss
+    got = np.mean([r[3] for r in res], axis=0)
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-6)
+    for k, v in model.state_dict().items():
+        a, b0, b1 = v.detach().cpu().numpy(), res[0][4][k], res[1][4][k]
+        np.testing.assert_array_equal(b0, b1)                   # replicas stay bit-identical
+        if v.is_floating_point():
+            err = float(np.linalg.norm(b0 - a) / max(np.linalg.norm(a), 1e-12))
+            assert err < 5e-3, (k, err)
