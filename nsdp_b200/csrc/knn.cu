@@ -9,6 +9,13 @@
 // split over S threads per query (more parallelism than M alone provides) and a second tiny kernel
 // merges the S sorted partial lists.
 //
+// Insertion into the sorted register list costs ~3 instructions per slot and — one query per thread — the whole warp pays
+// for it whenever ANY lane has a candidate, which early in a scan is almost every step (P = min(1, 32 k / t) at step t: at
+// the model's 4096 x 4096 / k = 10 site insertion, not distance evaluation, was 4/5 of the kernel). Candidates that beat
+// the thread's threshold (its k-th best distance as of the last flush) are therefore BUFFERED in shared memory and the lists
+// are updated in batches, when some lane's buffer fills up: the same insertions in the same order (a stale threshold only
+// admits extra candidates, which the insertion re-checks), a fraction of the divergent passes.
+//
 // Parity contract: distance = ((dx*dx + dy*dy) + dz*dz) with dx = query - ref, every operation rounded
 // separately (no FMA) exactly like torch's elementwise kernels; order = ascending (distance, index), i.e.
 // the stable order torch's unstable argsort leaves undefined on ties. Index tensors are int32.
@@ -22,6 +29,8 @@ namespace nsdp {
 
 constexpr int kKnnThreads = 128;
 constexpr int kKnnChunk = 1024;  // reference points staged per shared-memory tile (12 KB)
+constexpr int kKnnBuf = 8;       // buffered candidates per thread (8 KB of shared memory per block)
+constexpr int kKnnStep = 4;      // reference points between two "is some buffer nearly full" votes
 
 template <int KMAX>
 __device__ __forceinline__ void knn_insert(float (&dist)[KMAX], int (&id)[KMAX], float d, int j) {
@@ -45,6 +54,8 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
                 int split_len, int32_t *__restrict__ out_idx, float *__restrict__ out_d2,
                 float *__restrict__ part_d, int32_t *__restrict__ part_i) {
   __shared__ float tile[kKnnChunk * 3];
+  __shared__ float buf_d[kKnnBuf][kKnnThreads];
+  __shared__ int buf_i[kKnnBuf][kKnnThreads];
   const int b = blockIdx.z, s = blockIdx.y;
   const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
   const bool active = qi < M;
@@ -61,6 +72,19 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
     dist[i] = FLT_MAX;
     id[i] = 0x7fffffff;
   }
+  int nbuf = 0;              // candidates waiting in this thread's column of the buffer
+  float tau = FLT_MAX;       // k-th best distance as of the last flush
+  auto flush = [&]() {
+    const int most = __reduce_max_sync(0xffffffffu, nbuf);
+    for (int c = 0; c < most; ++c) {
+      if (c < nbuf) {
+        const float d = buf_d[c][threadIdx.x];
+        if (d < dist[KMAX - 1]) knn_insert<KMAX>(dist, id, d, buf_i[c][threadIdx.x]);
+      }
+    }
+    nbuf = 0;
+    tau = dist[KMAX - 1];
+  };
   // +inf distances must still be selectable when N is tiny: FLT_MAX sentinels lose against any finite d,
   // and genuine inf/NaN distances are never inserted (same as "sorted last"). A query or cloud with non-finite
   // coordinates (a diverging canonicaliser in FlowArbitrary feeds network OUTPUTS into this search) therefore leaves
@@ -73,17 +97,27 @@ knn_scan_kernel(const float *__restrict__ query, const float *__restrict__ ref, 
     __syncthreads();
     for (int t = threadIdx.x; t < cnt * 3; t += kKnnThreads) tile[t] = r[(size_t)base * 3 + t];
     __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const float dx = __fsub_rn(qx, tile[t * 3 + 0]);
-        const float dy = __fsub_rn(qy, tile[t * 3 + 1]);
-        const float dz = __fsub_rn(qz, tile[t * 3 + 2]);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (d < dist[KMAX - 1]) knn_insert<KMAX>(dist, id, d, base + t);
+    // whole warps run the loop (inactive lanes never produce candidates): the flush votes are warp-wide
+    for (int t0 = 0; t0 < cnt; t0 += kKnnStep) {
+      if (__any_sync(0xffffffffu, nbuf > kKnnBuf - kKnnStep)) flush();
+#pragma unroll
+      for (int u = 0; u < kKnnStep; ++u) {
+        const int t = t0 + u;
+        if (t < cnt) {
+          const float dx = __fsub_rn(qx, tile[t * 3 + 0]);
+          const float dy = __fsub_rn(qy, tile[t * 3 + 1]);
+          const float dz = __fsub_rn(qz, tile[t * 3 + 2]);
+          const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          if (active && d < tau) {
+            buf_d[nbuf][threadIdx.x] = d;
+            buf_i[nbuf][threadIdx.x] = base + t;
+            ++nbuf;
+          }
+        }
       }
     }
   }
+  flush();
   if (!active) return;
   if (S == 1) {
     int32_t *oi = out_idx + ((size_t)b * M + qi) * k;

@@ -2,7 +2,7 @@
 set -u
 mkdir -p gpurun_out
 for s in 0 1 2 3 8; do NSDP_KNN_SPLITS=$s timeout 120 python tools/microbench_knn.py 2>&1 | tail -1; done
-timeout 600 python -m pytest tests/test_gpu_graph.py tests/test_gpu_vattn.py tests/test_gpu_mlp.py -m gpu -q > gpurun_out/pytest_g.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests/test_gpu_graph.py tests/test_gpu_vattn.py tests/test_gpu_mlp.py tests/test_gpu_index_kernels.py tests/test_gpu_multi.py -m gpu -q > gpurun_out/pytest_g.log 2>&1; echo "pytest rc=$?"
 grep -E "passed|failed|FAILED|ERROR|^E " gpurun_out/pytest_g.log | tail -10
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-reference > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err; echo "bench rc=$?"
 python - <<PY
