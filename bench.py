@@ -43,9 +43,19 @@ WORKLOAD = "configs[1]: forward-deformation TDNet, batch 8 shapes x 4096 surface
 # (delta MLP 2*3*200 + 2*200*200, gamma MLP 2*2*200*200); the global row is a per-shape constant. Backward = 2x.
 VATTN_DEC_FWD_FLOP_PER_QUERY = 7 * (2 * 3 * 200 + 2 * 200 * 200) + 7 * (2 * 2 * 200 * 200)
 VATTN_DEC_BWD_FLOP_PER_QUERY = 2 * VATTN_DEC_FWD_FLOP_PER_QUERY
-# dram__bytes_read.sum + dram__bytes_write.sum of one decoder-attention backward op (13 chain + 13 reduction launches), from the
-# ncu --set full captures summarised in profiles/ncu_r1_summary.md
-NCU_TRAFFIC_BYTES_PER_OP = 34.8e9
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one decoder-attention backward op, summed by tools/make_profiles_r2.py
+    over every launch of the op in an ncu run of the CURRENT kernels (profiles/ncu_r2_traffic.json, profiles/ncu_r2_summary.md);
+    None when the file is missing. It cannot be measured live: DRAM counters need the profiler."""
+    path = os.path.join(ROOT, "profiles", "ncu_r2_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return float(t["traffic_bytes"]), t.get("staging", "?")
+    except Exception:
+        return None, "?"
 
 
 def emit_line(line: dict) -> None:
@@ -468,19 +478,26 @@ def run_ours(args):
         # products (2 M-tiles x 3 terms) + 2 table-gradient products (2 terms) over 8 k-steps of 16 rows
         mma = 2 * 128 * 208 * 16
         tiles = B_PER_GPU * ((N_QUERY + 15) // 16)
-        executed = tiles * mma * ((6 * 13 * 3 + 28) + 8 * (3 * 2 * 3 + 2 * 2))   # recompute path (SAVE_ACTIVATIONS off)
+        fp16_staging = ops.get_stage_format() == "fp16"
+        red_terms_w, red_terms_t = (1, 1) if fp16_staging else (3, 2)
+        executed = tiles * mma * ((6 * 13 * 3 + 28) + 8 * (3 * 2 * red_terms_w + 2 * red_terms_t))   # recompute path (SAVE_ACTIVATIONS off)
+        traffic, traffic_fmt = ncu_traffic()
         executed_tflops = executed / (bwd_ms * 1e-3) / 1e12
         roof = {"kernel": "nsdp_vattn_bwd_f32 for the decoder cross-attention (D=200, 7+1 rows/query): tcgen05 one-hot chain "
-                          "kernel vattn_bwd_oh_kernel (13 segment launches) + split-K gradient reduction dw_tc_kernel (weight and "
-                          "per-shape table gradients), timed as one op with CUDA events on the launching stream",
+                          "kernel vattn_bwd_oh_kernel (7 segment launches of 4144 tiles) + split-K gradient reduction dw_tc_kernel "
+                          "(weight and per-shape table gradients from " + ("fp16" if fp16_staging else "bf16 hi+lo") + "-staged operand "
+                          "tiles), timed as one op with CUDA events on the launching stream (eager instrumented steps)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES_PER_OP, "peak_source": peaks["source"],
+                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic if traffic_fmt == ("fp16" if fp16_staging else "bf16x2") else None,
+                "traffic_source": "profiles/ncu_r2_traffic.json (ncu DRAM counters summed over every launch of the op; not measurable live)",
+                "peak_source": peaks["source"],
                 "launch_ms": bwd_ms, "flop_per_launch": flops["vattn_bwd"],
                 "executed_mma_tflops": executed_tflops, "executed_frac": executed_tflops / peaks["bf16_tflops"],
                 "note": "achieved counts ALGORITHMIC flops (SURVEY 8d: 2 x 1.6884 MFLOP per query); the tensor pipe executes "
-                        "~6.9x that (bf16x3 split precision 3x, forward recompute 1.5x, 200->208 padding, one-hot table "
-                        "products), reported as executed_mma_tflops; the reduction kernel streams the staged operand tiles at "
-                        "HBM speed (profiles/)",
+                        "~5.5x that (bf16x3 split precision 3x on the chain, forward recompute 1.5x, 200->208 padding, one-hot table "
+                        "products, single-term fp16 reduction), reported as executed_mma_tflops; the chain kernel is serial per "
+                        "tile (GEMM -> epilogue -> GEMM, 39 % tensor-pipe active under ncu), the reduction streams the staged "
+                        "tiles from HBM (profiles/ncu_r2_summary.md)",
                 "share_of_step": dec_bwd["ms"] / prof_steps / prof_step_ms,
                 "top_kernel_by_time": top[0],
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,

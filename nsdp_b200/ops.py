@@ -40,6 +40,10 @@ def set_stage_format(fmt: str) -> str:
     return ("bf16x2", "fp16")[_lib.lib().nsdp_set_stage_format(code)]
 
 
+def get_stage_format() -> str:
+    return ("bf16x2", "fp16")[_lib.lib().nsdp_set_stage_format(-1)]
+
+
 TIMING = False     # when True every kernel call below is bracketed by CUDA events on the launching stream
 _TIMED = []        # (name, start_event, end_event)
 
