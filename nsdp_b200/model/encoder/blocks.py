@@ -104,6 +104,12 @@ class ElementwiseMLP(nn.Module):
         self.bn3 = nn.BatchNorm1d(dim)
 
     def forward(self, x):
+        if self.training and type(self.bn1) is not nn.BatchNorm1d:
+            # optional syncbn mode (nsdp_b200.dist.convert_sync_batchnorm): the statistics span all ranks, one collective per
+            # BatchNorm, so the three layers run one by one
+            h = F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, x)))
+            h = F.relu(_bn_rows(self.bn2, _pointwise(self.conv2, h)))
+            return _bn_rows(self.bn3, x + h)
         # one fused op: 4 kernels forward / 7 backward (csrc/emlp.cu) instead of the ~12 / ~30 cuDNN + elementwise launches
         return ops.elementwise_mlp(x, self.conv1, self.bn1, self.conv2, self.bn2, self.bn3)
 
