@@ -280,7 +280,8 @@ static int launch(const nsdp_mlp_args &a, float *out, void *workspace, size_t ws
     occ = occ < by_smem ? occ : by_smem;
     occ = occ < by_threads ? occ : by_threads;
     occ = occ < by_tmem ? occ : by_tmem;
-    if (const char *env = getenv("NSDP_MLP_CTAS_PER_SM")) occ = atoi(env);   // tuning experiments
+    static const int forced_occ = [] { const char *env = getenv("NSDP_MLP_CTAS_PER_SM"); return env ? atoi(env) : 0; }();
+    if (forced_occ > 0) occ = forced_occ;   // tuning experiments
     per_sm = occ < 1 ? 1 : occ;
   }
   const long long tiles = ceil_div((long long)a.R, 128ll);
