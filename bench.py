@@ -498,10 +498,10 @@ def run_ours(args):
                         "products, single-term fp16 reduction), reported as executed_mma_tflops; the chain kernel is serial per "
                         "tile (GEMM -> epilogue -> GEMM, 39 % tensor-pipe active under ncu), the reduction streams the staged "
                         "tiles from HBM (profiles/ncu_r2_summary.md)",
-                "share_of_step": dec_bwd["ms"] / prof_steps / prof_step_ms,
+                "share_of_step": bwd_ms / (ms_total / args.steps),
                 "top_kernel_by_time": top[0],
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,
-                               "share_of_step": dec_fwd["ms"] / prof_steps / prof_step_ms},
+                               "share_of_step": fwd_ms / (ms_total / args.steps)},
                 "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(summary.items())}}
         if world == 1 and not c3:
             try:
