@@ -272,3 +272,49 @@ def test_flow_arbitrary_training_step(golden, schemas):
     names = [n for n, _ in model.named_parameters()]
     idx = names.index("model_canonicalize.decoder.fc_out.weight")
     assert norms[idx] > 0 and abs(norms[idx] / ref[idx] - 1) < 5e-2
+
+
+def test_flow_arbitrary_full_size_step_and_stagewise_forward(schemas):
+    """BASELINE configs[2] at its real per-GPU size: FlowArbitrary with 4 shapes x 4096 surface points x 50 000 queries.
+    (a) one training step runs (finite loss, every trained parameter receives a finite gradient, peak memory far below the
+    reference's ~40 GB of saved activations); (b) shape 0, eval mode, against the CPU oracle stage by stage: canonicalised
+    queries / surface free-running, deformation teacher-forced with the oracle's stage-1 coordinates (FPS / k-NN on stage-1
+    OUTPUTS are discontinuous), all within the 1e-4 flow tolerance."""
+    from nsdp_b200.model.utils import compute_l2_error
+    B, N, Q = 4, 4096, 50000
+    model = _model(schemas, "arbitrary").train()
+    b = synth.forward_batch(B, N, Q, seed=1234, fp16_grid=True)
+    s = b["surface_samples_inputs"].to(DEV)
+    src, tgt, mask = s[:, :, 0:3], s[:, :, 3:6], s[:, :, 6:7]
+    torch.cuda.reset_peak_memory_stats()
+    pred = model(b["space_samples_src"].to(DEV), src, tgt, mask)
+    assert pred.shape == (B, Q, 3)
+    loss = compute_l2_error(pred, b["space_samples_tgt"].to(DEV))
+    loss.backward()
+    assert np.isfinite(loss.item())
+    missing = [k for k, p in model.named_parameters() if p.grad is None and not any(
+        t in k for t in ("transformer_begin.w_qs", "transformer_begin.w_ks", "transformer_begin.w_vs"))]
+    # the canonicalise net's pos_only first block never uses its q/k/v weights (model/encoder/blocks.py:119,126)
+    assert all(k.startswith("model_deform.") is False for k in missing) and len(missing) == 0, missing[:5]
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    assert torch.cuda.max_memory_allocated() < 20 * 2 ** 30
+    del pred, loss
+    model.zero_grad(set_to_none=True)
+    # ---- (b) stage-wise forward of shape 0 against the oracle ------------------------------------------------------------
+    model.eval()
+    cfg = synth.make_config("arbitrary")["model"]
+    sd = synth.named_state_dict([(k, s_) for k, s_ in schemas["arbitrary"]], seed=0)
+    q0, src0 = b["space_samples_src"][:1], b["surface_samples_inputs"][:1, :, 0:3].contiguous()
+    rest0 = b["surface_samples_inputs"][:1, :, 3:7]
+    with torch.no_grad():
+        want_space = orc.tdnet_forward(sd, "model_canonicalize.", q0, src0, cfg, True)
+        want_surf = orc.tdnet_forward(sd, "model_canonicalize.", src0, src0, cfg, True)
+        want_flow = orc.tdnet_forward(sd, "model_deform.", want_space, torch.cat([want_surf, rest0], -1).contiguous(), cfg, False)
+        cano, deform = model.model_canonicalize, model.model_deform
+        enc = cano.encode(src0.to(DEV))
+        got_space = cano.decode(q0.to(DEV), enc)
+        got_surf = cano.decode(src0.to(DEV), enc)
+        got_flow = deform(want_space.to(DEV), torch.cat([want_surf, rest0], -1).contiguous().to(DEV))
+    assert _mean_l2(got_space.cpu().numpy(), want_space.numpy()) < TOL
+    assert _mean_l2(got_surf.cpu().numpy(), want_surf.numpy()) < TOL
+    assert _mean_l2(got_flow.cpu().numpy(), want_flow.numpy()) < TOL
