@@ -49,9 +49,10 @@ class PointTransformerEncoder(nn.Module):
             raise NotImplementedError("intermediate point-cloud dumps are a debugging aid of the reference "
                                       "(pointransformer.py:94-136) and are not part of the hot path")
         if self.has_features:
-            feats = self.enc_sdf(xyz[:, :, 3:])
+            raw = xyz[:, :, 3:]
+            feats = self.enc_sdf(raw)
             xyz = xyz[:, :, :3].contiguous()
-            feats = self.transformer_begin(xyz, feats)
+            feats = self.transformer_begin(xyz, feats, feats_from=(raw, self.enc_sdf))
         else:
             feats = self.transformer_begin(xyz)
 
