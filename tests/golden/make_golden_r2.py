@@ -8,7 +8,7 @@
    training batch of make_golden.py. Tensors with more than 200 rows per shape keep every 8th row, the others every 2nd (consumers apply `thin` too).
 2. Forward-net training step in fp64 (the reference with .double(): the TRUTH SURVEY 8d's "< 1e-3 vs fp64" bar refers to),
    with queries that sit on a ReLU kink masked out of the loss (`fw64_keep`): prediction, d/d query, d/d surface, and
-   EVERY parameter gradient — a few tensors in full, all of them as norm + 4 seeded random projections <g, r_k>
+   EVERY parameter gradient — a few tensors in full, all of them as norm + 16 seeded random projections <g, r_k>
    (r_k ~ N(0,1), `projection_vectors`), so that consumers hold every tensor to a relative-L2 bar without an 18 MB fixture.
 3. FlowArbitrary training step, STAGED (model/flow_arbitrary.py:15-27): (a) stage-1 outputs of the fp32 reference in train
    mode; (b) stage 2 in fp64 teacher-forced with (a) -> loss, gradients reaching the stage-1 outputs, deform-net parameter
@@ -34,7 +34,7 @@ from oracle import tdnet_oracle as orc  # noqa: E402
 
 KINK = 1e-4   # relative pre-activation margin below which a query is left out of gradient comparisons (see main, part 2)
 
-NPROJ = 4
+NPROJ = 16
 TRACED = ("transformer_begin", "transition_downs.", "elementwise_extras.", "transformer_downs.", "elementwise.",
           "final_transformers.", "final_elementwise.")
 FULL_GRADS = ("decoder.fc_out.weight", "decoder.ct1.fc_gamma.0.weight", "decoder.ct1.fc_delta.0.weight", "decoder.ct1.w_ks.weight",

@@ -7,7 +7,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 
-NPROJ = 4
+NPROJ = 16
 
 
 def projection_vectors(name: str, numel: int) -> np.ndarray:
@@ -26,7 +26,7 @@ def rel(a, ref) -> float:
 
 def check_param_grads(named_grads: dict, gold, tag: str, full_tol: float, proj_tol: float, skip=lambda n: False):
     """Every parameter of the `tag` section of the fixture: tensors stored in full are held to `full_tol` (relative L2); all
-    others through their 4 seeded projections: rms_k |<g - g_ref, r_k>| / ||g_ref|| is an unbiased estimate of the
+    others through their 16 seeded projections: rms_k |<g - g_ref, r_k>| / ||g_ref|| is an unbiased estimate of the
     relative L2 error, held to `proj_tol`. Returns the worst (name, value) for the report."""
     names = [str(n) for n in gold[f"{tag}_names"]]
     worst = ("", 0.0)

@@ -163,12 +163,14 @@ def test_training_step_every_gradient_against_fp64_truth(golden_r2, schemas, imp
     e_ds = rel(surf.grad.cpu().numpy(), g["fw64_dsurf"])
     assert e_dq < 1e-3 and e_ds < 1e-3, (e_dq, e_ds)
     grads = {k: (None if p.grad is None else p.grad.cpu().numpy()) for k, p in model.named_parameters()}
-    # tensors kept in full: 1e-3 on both kernel families. Projection-estimated tensors (4 projections: the estimate itself
-    # scatters by ~35 %): 1.5e-3 on the fp32 kernels; 3e-3 on the tcgen05 kernels, whose bf16x3 products carry a ~3e-6
-    # relative error into every ReLU pre-activation of the ENCODER (2.5 M of them per shape in a full-attention block) —
-    # mask flips there cannot be left out of the loss. tools/kink_noise_emulation.py reproduces the effect on the CPU:
-    # the fp32 oracle plus 3e-6 noise on the pre-activations lands at 0.6 - 1.3e-3 on the same tensors (measured).
-    worst = check_param_grads(grads, g, "fw64", 1e-3, 1.5e-3 if impl == 1 else 3e-3)
+    # tensors kept in full: 1e-3 on both kernel families. Projection-estimated tensors (16 projections: the estimate itself
+    # scatters by ~18 %): 3e-3. ReLU mask flips inside the ENCODER (2.5 M pre-activations per shape in a full-attention block)
+    # cannot be left out of the loss, and ANY change of fp32 rounding re-rolls them: on encoder.final_transformers.0.fc_gamma.0
+    # the reference's own fp32 run is 3e-4 from the truth, the fp32 CUDA-core kernels 8e-4 .. 1.7e-3 depending on how the first
+    # block's projections are associated, the tcgen05 kernels (bf16x3: ~3e-6 on every pre-activation) 1.7e-3.
+    # tools/kink_noise_emulation.py reproduces the effect on the CPU: the fp32 oracle plus 3e-6 noise on the pre-activations
+    # lands at 0.6 - 1.3e-3 on the same tensors (measured).
+    worst = check_param_grads(grads, g, "fw64", 1e-3, 3e-3)
     print(f"[impl {impl}] d/dq {e_dq:.2e} (reference fp32: {float(g['fw64_ref32err_dq']):.2e}), d/dsurf {e_ds:.2e} "
           f"(reference fp32: {float(g['fw64_ref32err_dsurf']):.2e}), worst parameter gradient {worst}")
 
@@ -303,9 +305,10 @@ def test_flow_arbitrary_full_size_step_and_stagewise_forward(schemas):
     del pred, loss
     model.zero_grad(set_to_none=True)
     # ---- (b) stage-wise forward of shape 0 against the oracle ------------------------------------------------------------
-    model.eval()
     cfg = synth.make_config("arbitrary")["model"]
     sd = synth.named_state_dict([(k, s_) for k, s_ in schemas["arbitrary"]], seed=0)
+    model.load_state_dict(sd)          # the training-mode pass above moved the BatchNorm running statistics
+    model.eval()
     q0, src0 = b["space_samples_src"][:1], b["surface_samples_inputs"][:1, :, 0:3].contiguous()
     rest0 = b["surface_samples_inputs"][:1, :, 3:7]
     with torch.no_grad():
