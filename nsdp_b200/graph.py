@@ -44,12 +44,13 @@ class _Entry:
         self.lrs, self.launches, self.failed, self.opt_graph = None, 0, False, None
 
 
-def _signature(model, optimizer, data_dict):
-    sig = [id(optimizer), model.training]
-    for k in sorted(data_dict):
+def _signature(model, optimizer, data_dict, keys):
+    # what the captured launches depend on besides the values in the static buffers: input shapes, train / eval mode, which
+    # parameters are trainable (freezing a sub-network changes the autograd graph)
+    sig = [id(optimizer), model.training, sum(1 for p in model.parameters() if p.requires_grad)]
+    for k in keys:
         v = data_dict[k]
-        if torch.is_tensor(v):
-            sig.append((k, tuple(v.shape), v.dtype, str(v.device)))
+        sig.append((k, tuple(v.shape), v.dtype, str(v.device)))
     return tuple(sig)
 
 
@@ -66,7 +67,7 @@ def _capturable(optimizer) -> bool:
     return isinstance(optimizer, torch.optim.Adam) and all(g.get("capturable", False) for g in optimizer.param_groups)
 
 
-def _usable(model, optimizer, data_dict) -> bool:
+def _usable(model, optimizer, data_dict, keys) -> bool:
     if not ENABLED or ops.TIMING:
         return False
     from nsdp_b200 import dist
@@ -74,11 +75,13 @@ def _usable(model, optimizer, data_dict) -> bool:
         return False
     if dist.is_active() and any(isinstance(m, dist.SyncBatchNorm1d) for m in model.modules()):
         return False          # syncbn mode issues collectives inside forward / backward: stays eager
-    tensors = [v for v in data_dict.values() if torch.is_tensor(v)]
-    return bool(tensors) and all(v.is_cuda for v in tensors) and not torch.cuda.is_current_stream_capturing()
+    tensors = [data_dict.get(k) for k in keys]
+    return bool(tensors) and all(torch.is_tensor(v) and v.is_cuda for v in tensors) and not torch.cuda.is_current_stream_capturing()
 
 
-def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
+def graphed_train_step(model, optimizer, data_dict, forward_backward, finish, keys):
+    """`keys`: the entries of data_dict the step reads (the datasets put ~20 tensors into a sample, the step uses 3): only these
+    get static buffers inside the graph; nothing else of data_dict reaches the captured code."""
     from nsdp_b200 import dist
     split = dist.is_active()          # data parallel: the collective and the optimizer stay outside the graph
 
@@ -87,10 +90,10 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
         finish(model, optimizer)
         return loss
 
-    if not _usable(model, optimizer, data_dict):
+    if not _usable(model, optimizer, data_dict, keys):
         return eager_fn(model, optimizer, data_dict).item()
     per_model = _STATE.setdefault(model, {})
-    sig = _signature(model, optimizer, data_dict)
+    sig = _signature(model, optimizer, data_dict, keys)
     e = per_model.get(sig)
     if e is None:
         e = per_model[sig] = _Entry()
@@ -111,14 +114,14 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
         try:
             if split:
                 dist.set_overlap(model, False)       # no collectives from autograd hooks while capturing / replaying
-                _capture(e, model, optimizer, data_dict, forward_backward)
+                _capture(e, model, optimizer, data_dict, forward_backward, keys)
                 if _capturable(optimizer):           # the fused Adam launches as a second, tiny graph after the collective
                     og = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(og):
                         optimizer.step()
                     e.opt_graph = og
             else:
-                _capture(e, model, optimizer, data_dict, eager_fn)
+                _capture(e, model, optimizer, data_dict, eager_fn, keys)
             e.lrs = lrs
         except Exception as exc:   # noqa: BLE001 — never lose a training step over an optimisation
             e.failed = True
@@ -142,9 +145,9 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish):
     return e.loss.item()
 
 
-def _capture(e: _Entry, model, optimizer, data_dict, eager_fn) -> None:
-    static = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
-    passthrough = {k: v for k, v in data_dict.items() if not torch.is_tensor(v)}
+def _capture(e: _Entry, model, optimizer, data_dict, eager_fn, keys) -> None:
+    static = {k: data_dict[k].clone() for k in keys}
+    passthrough = {}
     # gradients must be (re)created INSIDE the capture so that they live in the graph's memory pool (single GPU); under
     # data parallelism they are views of the flat bucket buffer, which exists since the first warm-up step
     from nsdp_b200 import dist

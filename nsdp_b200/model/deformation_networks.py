@@ -65,7 +65,8 @@ def _finish_step(model, optimizer):
 def train_on_batch_with_cano(model, optimizer, data_dict, config):
     """deformation_networks.py:63-77. The step itself is `_train_step_with_cano`; on a GPU it is captured into a CUDA graph
     after a few calls and replayed (nsdp_b200/graph.py) — same arithmetic, one launch per step."""
-    return graphed_train_step(model, optimizer, data_dict, _train_step_with_cano, _finish_step)
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_cano, _finish_step,
+                              keys=("surface_samples_inputs", "space_samples_src", "space_samples_tgt"))
 
 
 @torch.no_grad()

@@ -80,7 +80,8 @@ def _finish_step(model, optimizer):
 
 def train_on_batch_with_arbitrary(model, optimizer, data_dict, config):
     """flow_arbitrary.py:30-48; captured into a CUDA graph after a few calls (nsdp_b200/graph.py)."""
-    return graphed_train_step(model, optimizer, data_dict, _train_step_with_arbitrary, _finish_step)
+    return graphed_train_step(model, optimizer, data_dict, _train_step_with_arbitrary, _finish_step,
+                              keys=("surface_samples_inputs", "space_samples_src", "space_samples_tgt"))
 
 
 @torch.no_grad()
