@@ -88,18 +88,12 @@ class TransformerBlock(nn.Module):
         self.k = k
         self.group_all = group_all
 
-    def neighbours(self, xyz):
-        """The block's k-NN index tensor (None for full attention): a function of the coordinates only."""
-        return None if self.group_all else knn_indices(xyz, xyz, min(self.k, xyz.shape[1]))
-
-    def forward(self, xyz, feats=None, feats_from=None, idx="compute"):
-        """Optimisation hints of the mirror (the reference signature is (xyz, feats)): `feats_from = (x_in, lin)`, the caller's
-        statement that feats == lin(x_in) with a narrow x_in (see _fused_linear_through); `idx`, the block's neighbour
-        indices computed ahead of time by `neighbours(xyz)` (PointTransformerEncoder does that on a side stream)."""
+    def forward(self, xyz, feats=None, feats_from=None):
+        """`feats_from = (x_in, lin)`: the caller's statement that feats == lin(x_in) with a narrow x_in (see
+        _fused_linear_through); an optimisation hint of the mirror, the reference signature is (xyz, feats)."""
         B, n, _ = xyz.shape
         xyz = xyz.contiguous()
-        if isinstance(idx, str):
-            idx = self.neighbours(xyz)
+        idx = None if self.group_all else knn_indices(xyz, xyz, min(self.k, n))
         w = fold_pair_mlps(self.fc_delta, self.fc_gamma)
         if self.pos_only:
             res = ops.vector_attention(xyz, xyz, idx, None, None, None, sign=1.0, **w)
@@ -159,18 +153,13 @@ class TransformerSetAbstraction(nn.Module):
         self.w_ks2 = nn.Linear(dim, dim, bias=False)
         self.w_vs2 = nn.Linear(dim, dim, bias=False)
 
-    @torch.no_grad()
-    def sample_and_group(self, xyz):
-        """FPS picks, their coordinates (detached, as in blocks.py:282-285) and the k-NN of every pick in the full cloud:
-        functions of the coordinates only."""
-        xyz = xyz.detach().contiguous()
-        fps_idx = ops.furthest_point_sampling(xyz, self.npoint)
-        new_xyz = index_points(xyz, fps_idx).contiguous()
-        return fps_idx, new_xyz, knn_indices(new_xyz, xyz, min(self.nneigh, xyz.shape[1]))
-
-    def forward(self, xyz, points, pre=None):
+    def forward(self, xyz, points):
         xyz = xyz.contiguous()
-        fps_idx, new_xyz, idx = pre if pre is not None else self.sample_and_group(xyz)
+        N = xyz.shape[1]
+        with torch.no_grad():
+            fps_idx = ops.furthest_point_sampling(xyz.detach(), self.npoint)
+            new_xyz = index_points(xyz.detach(), fps_idx).contiguous()  # detached, as in blocks.py:282-285
+            idx = knn_indices(new_xyz, xyz, min(self.nneigh, N))
         centre = index_points(points, fps_idx)
 
         w1 = fold_pair_mlps(self.fc_delta1, self.fc_gamma1)
@@ -234,5 +223,5 @@ class TransitionDown(nn.Module):
         else:
             raise ValueError("Set Abstraction type " + type + " unknown!")
 
-    def forward(self, xyz, feats, pre=None):
-        return self.sa(xyz, feats) if pre is None else self.sa(xyz, feats, pre=pre)
+    def forward(self, xyz, feats):
+        return self.sa(xyz, feats)

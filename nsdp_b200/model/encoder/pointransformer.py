@@ -44,65 +44,28 @@ class PointTransformerEncoder(nn.Module):
             [TransformerBlock(d_transformer, 2 * nneighbor, group_all=full_SA) for _ in range(nfinal_transformers)])
         self.final_elementwise = nn.ModuleList([ElementwiseMLP(dim=d_transformer) for _ in range(nfinal_transformers)])
 
-    def _index_plan(self, xyz):
-        """Every FPS / k-NN index tensor of the encoder after the first block depends on the INPUT coordinates only (the
-        down-sampled clouds are FPS picks of the input). They are computed up front on a side stream — FPS at 4096 points is
-        0.45 ms on 8 SMs, the later k-NN searches are latency-bound — while the main stream runs the first attention block;
-        inside a captured CUDA graph this becomes a parallel branch. Returns (plan, event to wait for)."""
-        if not hasattr(self.transition_downs[0].sa, "sample_and_group") or not xyz.is_cuda:
-            return None, None
-        main = torch.cuda.current_stream(xyz.device)
-        side = self.__dict__.get("_side_stream")
-        if side is None or side.device != xyz.device:
-            if torch.cuda.is_current_stream_capturing():
-                return None, None                     # no stream creation while capturing (warm-up calls create it)
-            side = self.__dict__["_side_stream"] = torch.cuda.Stream(xyz.device)
-        side.wait_stream(main)
-        plan = []
-        with torch.cuda.stream(side), torch.no_grad():
-            cur = xyz.detach()
-            for level, down in enumerate(self.transition_downs):
-                pre = down.sa.sample_and_group(cur)
-                cur = pre[1]
-                plan.append((pre, self.transformer_downs[level].neighbours(cur)))
-            final_idx = [blk.neighbours(cur) for blk in self.final_transformers]
-            done = side.record_event()
-        for pre, idx in plan:
-            for t in (*pre, idx):
-                if t is not None:
-                    t.record_stream(main)
-        for t in final_idx:
-            if t is not None:
-                t.record_stream(main)
-        return (plan, final_idx), done
-
     def forward(self, xyz, intermediate_out_path=None):
         if intermediate_out_path is not None:
             raise NotImplementedError("intermediate point-cloud dumps are a debugging aid of the reference "
                                       "(pointransformer.py:94-136) and are not part of the hot path")
-        coords = (xyz[:, :, :3] if self.has_features else xyz).contiguous()
-        plan, plan_done = self._index_plan(coords)
         if self.has_features:
             raw = xyz[:, :, 3:]
             feats = self.enc_sdf(raw)
-            xyz = coords
+            xyz = xyz[:, :, :3].contiguous()
             feats = self.transformer_begin(xyz, feats, feats_from=(raw, self.enc_sdf))
         else:
             feats = self.transformer_begin(xyz)
-        if plan_done is not None:
-            torch.cuda.current_stream(coords.device).wait_event(plan_done)
 
         for level, down in enumerate(self.transition_downs):
-            pre, idx = plan[0][level] if plan is not None else (None, "compute")
-            xyz, feats = down(xyz, feats, pre=pre)
+            xyz, feats = down(xyz, feats)
             feats = self.elementwise_extras[level](feats)
-            feats = self.transformer_downs[level](xyz, feats, idx=idx)
+            feats = self.transformer_downs[level](xyz, feats)
             if level == 0 and self.d_reduced != self.d_transformer:
                 feats = self.fc1(feats)
             feats = self.elementwise[level](feats)
 
-        for i, (block, mlp) in enumerate(zip(self.final_transformers, self.final_elementwise)):
-            feats = mlp(block(xyz, feats, idx=plan[1][i] if plan is not None else "compute"))
+        for block, mlp in zip(self.final_transformers, self.final_elementwise):
+            feats = mlp(block(xyz, feats))
 
         z = self.fc_middle(feats.max(dim=1)[0])
         return {"z": z, "anchors": xyz, "anchor_feats": feats}
