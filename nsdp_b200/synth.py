@@ -44,6 +44,17 @@ def make_config(model_type: str = "forward") -> dict:
                                        "weight_decay": 0.0}}
 
 
+def make_alt_config() -> dict:
+    """A NON-default model block: every knob the reference's blocks honour although no shipped YAML varies it (SURVEY App. A:
+    `full_SA: false` -> local final blocks with k = 2 * nneighbor, three down-sampling levels, other widths, `n_blocks`,
+    `nneigh`). Exercises the kernels' shape dispatch away from the one configuration the bench runs."""
+    cfg = make_config("forward")
+    cfg["model"]["encoder_kwargs"] = {"npoints_per_layer": [2000, 400, 128, 48], "nneighbor": 12, "nneighbor_reduced": 8,
+                                      "nfinal_transformers": 2, "d_transformer": 128, "d_reduced": 64, "full_SA": False}
+    cfg["model"]["decoder_kwargs"] = {"dim_inp": 128, "dim": 96, "nneigh": 5, "hidden_dim": 128, "out_dim": 3, "n_blocks": 3}
+    return cfg
+
+
 def make_ablation_config() -> dict:
     """The reference's ablation blocks behind the same registries: PointNet++-style encoder (max-pool set abstraction)
     and the interpolation decoder (model/encoder/__init__.py:4-7, model/decoder/__init__.py:5-8)."""

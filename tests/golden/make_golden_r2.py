@@ -10,6 +10,8 @@
    with queries that sit on a ReLU kink masked out of the loss (`fw64_keep`): prediction, d/d query, d/d surface, and
    EVERY parameter gradient — a few tensors in full, all of them as norm + 16 seeded random projections <g, r_k>
    (r_k ~ N(0,1), `projection_vectors`), so that consumers hold every tensor to a relative-L2 bar without an 18 MB fixture.
+1b. `alt_*`: eval forward of the live reference in a NON-default configuration (`synth.make_alt_config`: three down-sampling
+   levels, local final attention, other widths / neighbour counts / block counts) + its state_dict schema.
 3. FlowArbitrary training step, STAGED (model/flow_arbitrary.py:15-27): (a) stage-1 outputs of the fp32 reference in train
    mode; (b) stage 2 in fp64 teacher-forced with (a) -> loss, gradients reaching the stage-1 outputs, deform-net parameter
    gradients; (c) stage-1 backward in fp64 driven by (b)'s gradients -> canonicalise-net parameter gradients. Stage 2's
@@ -94,6 +96,21 @@ def main():
         tr = trace_encoder(m.encoder, lambda: m.encoder(b3["surface_samples_inputs"]))
     for k, v in tr.items():
         gold["trace_train::" + k] = v
+
+    # ---- 1b. a NON-default configuration (synth.make_alt_config): eval forward of the live reference ------------------------
+    acfg = synth.make_alt_config()
+    am, *_ = ref.build_model(acfg)
+    gold_schema = schema_of(am)
+    am.load_state_dict(synth.named_state_dict([(k, s_) for k, s_ in gold_schema], seed=4))
+    am.eval()
+    ab = synth.forward_batch(2, 1500, 300, seed=31, fp16_grid=True)
+    with torch.no_grad():
+        aenc = am.encoder(ab["surface_samples_inputs"])
+        gold["alt_flow"] = am(ab["space_samples_src"], ab["surface_samples_inputs"]).numpy()
+    gold["alt_z"] = aenc["z"].numpy()
+    gold["alt_anchors"] = aenc["anchors"].numpy()
+    gold["alt_schema_keys"] = np.array([k for k, _ in gold_schema])
+    gold["alt_schema_shapes"] = np.array([",".join(map(str, s_)) for _, s_ in gold_schema])
 
     # ---- 2. forward-net training step against fp64 TRUTH, kink rows masked out of the loss -----------------------------
     # Gradients are discontinuous where a ReLU pre-activation crosses 0: a 1e-7 perturbation flips the mask of a query that

@@ -323,3 +323,54 @@ def test_flow_arbitrary_full_size_step_and_stagewise_forward(schemas):
     assert _mean_l2(got_space.cpu().numpy(), want_space.numpy()) < TOL
     assert _mean_l2(got_surf.cpu().numpy(), want_surf.numpy()) < TOL
     assert _mean_l2(got_flow.cpu().numpy(), want_flow.numpy()) < TOL
+
+
+def test_non_default_configuration_forward_and_gradients(golden_r2):
+    """Every config knob the reference's blocks honour in ONE non-default model (synth.make_alt_config: three
+    down-sampling levels, local final attention with k = 2 * nneighbor, widths 64 / 128 / 96, 5 neighbours, 3 ResNet blocks):
+    the kernels' shape dispatch away from the bench configuration. Forward vs the live-reference fixture (anchors bit-exact,
+    flow 1e-4); training step vs the oracle's autograd on the CPU (loss, d/d query on non-kink rows, selected gradients)."""
+    from helpers_r2 import masked_l2, rel
+    g = golden_r2
+    schema = [(str(k), tuple(int(x) for x in str(s).split(",") if x)) for k, s in zip(g["alt_schema_keys"], g["alt_schema_shapes"])]
+    cfg = synth.make_alt_config()
+    model, *_ = build_model(cfg, device=DEV)
+    assert [(k, tuple(v.shape)) for k, v in model.state_dict().items()] == schema        # same schema as the reference builds
+    sd = synth.named_state_dict(schema, seed=4)
+    model.load_state_dict(sd)
+    model.eval()
+    b = synth.forward_batch(2, 1500, 300, seed=31, fp16_grid=True)
+    with torch.no_grad():
+        surf = b["surface_samples_inputs"].to(DEV)
+        enc = model.encode(surf)
+        out = model.decode(b["space_samples_src"].to(DEV), enc)
+    np.testing.assert_array_equal(enc["anchors"].cpu().numpy(), g["alt_anchors"])
+    np.testing.assert_allclose(enc["z"].cpu().numpy(), g["alt_z"], atol=1e-4, rtol=1e-3)
+    assert _mean_l2(out.cpu().numpy(), g["alt_flow"]) < TOL
+    # training step: fp64 oracle as the truth, kink queries masked out of the loss on both sides
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in sd64.items() if k.rsplit(".", 1)[-1] in ("weight", "bias")}
+    kink = {}
+    with torch.no_grad():
+        orc.tdnet_forward({k: v.detach().clone() for k, v in sd64.items()}, "", b["space_samples_src"].double(),
+                          b["surface_samples_inputs"].double(), cfg["model"], False, training=True, kink=kink)
+    keep = kink["margin"] > 1e-4
+    q64 = b["space_samples_src"].double().requires_grad_(True)
+    want = orc.tdnet_forward(sd64, "", q64, b["surface_samples_inputs"].double(), cfg["model"], False, training=True)
+    loss64 = masked_l2(want, b["space_samples_tgt"].double(), keep)
+    loss64.backward()
+    model.train()
+    q = b["space_samples_src"].to(DEV).requires_grad_(True)
+    pred = model(q, surf)
+    loss = masked_l2(pred, b["space_samples_tgt"].to(DEV), keep.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - loss64.item()) < 1e-5
+    assert _mean_l2(pred.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    k = keep.numpy()
+    assert rel(q.grad.cpu().numpy()[k], q64.grad.numpy()[k]) < 1e-3
+    grads = dict(model.named_parameters())
+    for name in ("decoder.fc_out.weight", "decoder.ct1.fc_gamma.0.weight", "decoder.ct1.w_ks.weight", "decoder.blocks.2.fc_0.weight",
+                 "encoder.fc_middle.0.weight", "encoder.final_transformers.1.w_vs.weight", "encoder.transition_downs.2.sa.fc_gamma2.0.weight",
+                 "encoder.transformer_begin.fc_delta.2.weight", "encoder.enc_sdf.weight", "encoder.elementwise.2.conv1.weight"):
+        e = rel(grads[name].grad.cpu().numpy(), params[name].grad.numpy())
+        assert e < 3e-3, (name, e)
