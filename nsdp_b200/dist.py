@@ -14,6 +14,7 @@ Optional `syncbn` mode (NSDP_B200_SYNCBN=1 or convert_sync_batchnorm(model)): ev
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Iterable, List, Optional
 
 import torch
@@ -161,13 +162,13 @@ class _GradBuckets:
                                "parameters with gradients changed between steps); set NSDP_B200_OVERLAP=0" % sorted(set(late)))
 
 
-_BUCKETS = {}  # id(model) -> _GradBuckets
+_BUCKETS = weakref.WeakKeyDictionary()  # model -> _GradBuckets (dies with the model: an id() can be reused)
 
 
 def _buckets_for(model) -> _GradBuckets:
-    bk = _BUCKETS.get(id(model))
+    bk = _BUCKETS.get(model)
     if bk is None:
-        bk = _BUCKETS[id(model)] = _GradBuckets(model, int(os.environ.get("NSDP_B200_BUCKET_BYTES", 4 << 20)))
+        bk = _BUCKETS[model] = _GradBuckets(model, int(os.environ.get("NSDP_B200_BUCKET_BYTES", 4 << 20)))
     return bk
 
 
