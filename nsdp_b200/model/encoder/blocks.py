@@ -73,6 +73,45 @@ def fold_pair_mlps(fc_delta: nn.Sequential, fc_gamma: nn.Sequential):
     )
 
 
+def fold_sites(sites):
+    """fold_pair_mlps + the `Wg0 @ W` projection folds for MANY attention sites at once. `sites` is a list of
+    (fc_delta, fc_gamma, [Linear, ...]): the Linears are the per-point projections that feed fc_gamma[0] (w_qs, w_ks, ...).
+    Sites of equal width are stacked and folded with batched products: the encoder has 10 sites of 2 widths, and folding
+    them one by one costs ~13 tiny launches per site forward and twice that backward (weights change every step, so the folds
+    are part of every step). Returns one (operands dict, [folded projection weights]) pair per site, equal to what
+    fold_pair_mlps / `wg0 @ w` give (same arithmetic, batched)."""
+    out = [None] * len(sites)
+    groups = {}
+    for i, (fd, fg, projs) in enumerate(sites):
+        groups.setdefault(fd[2].weight.shape[0], []).append(i)
+    for d, members in groups.items():
+        if len(members) == 1:
+            i = members[0]
+            fd, fg, projs = sites[i]
+            out[i] = (fold_pair_mlps(fd, fg), [fg[0].weight @ p.weight for p in projs])
+            continue
+        wd2 = torch.stack([sites[i][0][2].weight for i in members])            # (S, d, d)
+        bd2 = torch.stack([sites[i][0][2].bias for i in members])              # (S, d)
+        wg0 = torch.stack([sites[i][1][0].weight for i in members])
+        bg0 = torch.stack([sites[i][1][0].bias for i in members])
+        wg2 = torch.stack([sites[i][1][2].weight for i in members])
+        wd2t = wd2.transpose(1, 2).contiguous()
+        wpt = torch.bmm(wg0, wd2).transpose(1, 2).contiguous()
+        wg2t = wg2.transpose(1, 2).contiguous()
+        pc = torch.bmm(wg0, bd2.unsqueeze(-1)).squeeze(-1) + bg0
+        # projection folds: every (site, projection) pair is one batch entry
+        owner = [(s, p) for s, i in enumerate(members) for p in sites[i][2]]
+        folded = torch.bmm(wg0[[s for s, _ in owner]], torch.stack([p.weight for _, p in owner])) if owner else None
+        per_site = {s: [] for s in range(len(members))}
+        for n, (s, _) in enumerate(owner):
+            per_site[s].append(folded[n])
+        for s, i in enumerate(members):
+            fd = sites[i][0]
+            out[i] = (dict(wd0=fd[0].weight.contiguous(), bd0=fd[0].bias.contiguous(), wd2t=wd2t[s], wpt=wpt[s], wg2t=wg2t[s],
+                           pc=pc[s], vc=bd2[s]), per_site[s])
+    return out
+
+
 class TransformerBlock(nn.Module):
     """Local / global vector self-attention (reference: model/encoder/blocks.py:52-134)."""
 
@@ -88,18 +127,22 @@ class TransformerBlock(nn.Module):
         self.k = k
         self.group_all = group_all
 
-    def forward(self, xyz, feats=None, feats_from=None):
-        """`feats_from = (x_in, lin)`: the caller's statement that feats == lin(x_in) with a narrow x_in (see
-        _fused_linear_through); an optimisation hint of the mirror, the reference signature is (xyz, feats)."""
+    def fold_site(self):
+        """This block's entry for fold_sites()."""
+        return (self.fc_delta, self.fc_gamma, [] if self.pos_only else [self.w_qs, self.w_ks])
+
+    def forward(self, xyz, feats=None, feats_from=None, folded=None):
+        """Optimisation hints of the mirror (the reference signature is (xyz, feats)): `feats_from = (x_in, lin)`, the caller's
+        statement that feats == lin(x_in) with a narrow x_in (see _fused_linear_through); `folded`, this block's entry of
+        fold_sites() computed ahead of time together with the other blocks'."""
         B, n, _ = xyz.shape
         xyz = xyz.contiguous()
         idx = None if self.group_all else knn_indices(xyz, xyz, min(self.k, n))
-        w = fold_pair_mlps(self.fc_delta, self.fc_gamma)
+        w, fp = folded if folded is not None else fold_sites([self.fold_site()])[0]
         if self.pos_only:
             res = ops.vector_attention(xyz, xyz, idx, None, None, None, sign=1.0, **w)
         else:
-            wg0 = self.fc_gamma[0].weight
-            proj = (wg0 @ self.w_qs.weight, wg0 @ self.w_ks.weight, self.w_vs.weight)
+            proj = (fp[0], fp[1], self.w_vs.weight)
             if feats_from is not None and feats_from[0].shape[-1] * 4 <= feats.shape[-1]:
                 qp, kp, vp = _fused_linear_through(feats_from[0], feats_from[1], proj)
             else:
@@ -153,7 +196,11 @@ class TransformerSetAbstraction(nn.Module):
         self.w_ks2 = nn.Linear(dim, dim, bias=False)
         self.w_vs2 = nn.Linear(dim, dim, bias=False)
 
-    def forward(self, xyz, points):
+    def fold_site(self):
+        """Two entries for fold_sites(): (fc_delta1, fc_gamma1) and (fc_delta1, fc_gamma2)."""
+        return [(self.fc_delta1, self.fc_gamma1, [self.w_qs, self.w_ks]), (self.fc_delta1, self.fc_gamma2, [self.w_qs2, self.w_ks2])]
+
+    def forward(self, xyz, points, folded=None):
         xyz = xyz.contiguous()
         N = xyz.shape[1]
         with torch.no_grad():
@@ -162,20 +209,16 @@ class TransformerSetAbstraction(nn.Module):
             idx = knn_indices(new_xyz, xyz, min(self.nneigh, N))
         centre = index_points(points, fps_idx)
 
-        w1 = fold_pair_mlps(self.fc_delta1, self.fc_gamma1)
-        g10 = self.fc_gamma1[0].weight
-        g20 = self.fc_gamma2[0].weight
-        qp = F.linear(centre, g10 @ self.w_qs.weight)
+        (w1, (fq1, fk1)), (w2, (fq2, fk2)) = folded if folded is not None else fold_sites(self.fold_site())
+        qp = F.linear(centre, fq1)
         # the four projections of the full cloud (both attention stages) share their input: one GEMM
-        kp, vp, kp2, vp2 = _fused_linear(points, (g10 @ self.w_ks.weight, self.w_vs.weight, g20 @ self.w_ks2.weight,
-                                                  self.w_vs2.weight))
+        kp, vp, kp2, vp2 = _fused_linear(points, (fk1, self.w_vs.weight, fk2, self.w_vs2.weight))
         # rel = neighbour - centre (blocks.py:295) -> sign = -1
         res1 = ops.vector_attention(new_xyz, xyz, idx, qp, kp, vp, sign=-1.0, **w1)
         res1 = res1 + _pointwise(self.conv2, F.relu(_bn_rows(self.bn1, _pointwise(self.conv1, res1))))
         res1 = _bn_rows(self.bnorm0, res1)
 
-        w2 = fold_pair_mlps(self.fc_delta1, self.fc_gamma2)  # same delta MLP, second gamma MLP
-        qp2 = F.linear(res1, g20 @ self.w_qs2.weight)
+        qp2 = F.linear(res1, fq2)          # second stage: same delta MLP, second gamma MLP
         res2 = ops.vector_attention(new_xyz, xyz, idx, qp2, kp2, vp2, sign=-1.0, **w2)
 
         out = _bn_rows(self.bnorm1, res1 + res2) + centre
@@ -223,5 +266,5 @@ class TransitionDown(nn.Module):
         else:
             raise ValueError("Set Abstraction type " + type + " unknown!")
 
-    def forward(self, xyz, feats):
-        return self.sa(xyz, feats)
+    def forward(self, xyz, feats, folded=None):
+        return self.sa(xyz, feats) if folded is None else self.sa(xyz, feats, folded=folded)

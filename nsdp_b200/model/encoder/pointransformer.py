@@ -8,7 +8,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from nsdp_b200.model.encoder.blocks import ElementwiseMLP, TransformerBlock, TransitionDown
+from nsdp_b200.model.encoder.blocks import ElementwiseMLP, TransformerBlock, TransitionDown, fold_sites
 
 
 class PointTransformerEncoder(nn.Module):
@@ -44,28 +44,47 @@ class PointTransformerEncoder(nn.Module):
             [TransformerBlock(d_transformer, 2 * nneighbor, group_all=full_SA) for _ in range(nfinal_transformers)])
         self.final_elementwise = nn.ModuleList([ElementwiseMLP(dim=d_transformer) for _ in range(nfinal_transformers)])
 
+    def _fold_all(self):
+        """Kernel-ready weights of every attention site of the encoder in one batched pass (blocks.fold_sites)."""
+        keys, sites = ["begin"], [self.transformer_begin.fold_site()]
+        for level, down in enumerate(self.transition_downs):
+            if hasattr(down.sa, "fold_site"):                       # attentive set abstraction: two sites
+                keys += [("sa", level, 0), ("sa", level, 1)]
+                sites += down.sa.fold_site()
+            keys.append(("td", level))
+            sites.append(self.transformer_downs[level].fold_site())
+        for i, blk in enumerate(self.final_transformers):
+            keys.append(("final", i))
+            sites.append(blk.fold_site())
+        folded = dict(zip(keys, fold_sites(sites)))
+        for level in range(len(self.transition_downs)):
+            if ("sa", level, 0) in folded:
+                folded[("sa", level)] = (folded.pop(("sa", level, 0)), folded.pop(("sa", level, 1)))
+        return folded
+
     def forward(self, xyz, intermediate_out_path=None):
         if intermediate_out_path is not None:
             raise NotImplementedError("intermediate point-cloud dumps are a debugging aid of the reference "
                                       "(pointransformer.py:94-136) and are not part of the hot path")
+        folds = self._fold_all()
         if self.has_features:
             raw = xyz[:, :, 3:]
             feats = self.enc_sdf(raw)
             xyz = xyz[:, :, :3].contiguous()
-            feats = self.transformer_begin(xyz, feats, feats_from=(raw, self.enc_sdf))
+            feats = self.transformer_begin(xyz, feats, feats_from=(raw, self.enc_sdf), folded=folds["begin"])
         else:
-            feats = self.transformer_begin(xyz)
+            feats = self.transformer_begin(xyz, folded=folds["begin"])
 
         for level, down in enumerate(self.transition_downs):
-            xyz, feats = down(xyz, feats)
+            xyz, feats = down(xyz, feats, folded=folds.get(("sa", level)))
             feats = self.elementwise_extras[level](feats)
-            feats = self.transformer_downs[level](xyz, feats)
+            feats = self.transformer_downs[level](xyz, feats, folded=folds[("td", level)])
             if level == 0 and self.d_reduced != self.d_transformer:
                 feats = self.fc1(feats)
             feats = self.elementwise[level](feats)
 
-        for block, mlp in zip(self.final_transformers, self.final_elementwise):
-            feats = mlp(block(xyz, feats))
+        for i, (block, mlp) in enumerate(zip(self.final_transformers, self.final_elementwise)):
+            feats = mlp(block(xyz, feats, folded=folds[("final", i)]))
 
         z = self.fc_middle(feats.max(dim=1)[0])
         return {"z": z, "anchors": xyz, "anchor_feats": feats}
