@@ -101,7 +101,8 @@ def fold_sites(sites):
         pc = torch.bmm(wg0, bd2.unsqueeze(-1)).squeeze(-1) + bg0
         # projection folds: every (site, projection) pair is one batch entry
         owner = [(s, p) for s, i in enumerate(members) for p in sites[i][2]]
-        folded = torch.bmm(wg0[[s for s, _ in owner]], torch.stack([p.weight for _, p in owner])) if owner else None
+        # (no index tensors: a Python-list index would be a host -> device copy, which a CUDA-graph capture refuses)
+        folded = torch.bmm(torch.stack([wg0[s] for s, _ in owner]), torch.stack([p.weight for _, p in owner])) if owner else None
         per_site = {s: [] for s in range(len(members))}
         for n, (s, _) in enumerate(owner):
             per_site[s].append(folded[n])
