@@ -454,6 +454,7 @@ def run_ours(args):
     step_e2e()
     e2e_ms, _ = timed(step_e2e, args.steps)
 
+    peak_ours_gib = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)     # before the same-GPU reference run below
     total_q = world * B_PER_GPU * N_QUERY
     value = total_q * args.steps / (ms_total * 1e-3)
     e2e_value = total_q * args.steps / (e2e_ms * 1e-3)
@@ -526,7 +527,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "surface_pts": N_SURF, "queries": N_QUERY,
-                           "parallelism": f"dp{world}", "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "l2": "256 MiB buffer zeroed between steps (outside the event pairs)",
+                           "parallelism": f"dp{world}", "peak_memory_gib": peak_ours_gib, "l2": "256 MiB buffer zeroed between steps (outside the event pairs)",
                            "step_execution": graph_mode(), "bn": ("global-batch statistics (syncbn)" if os.environ.get("NSDP_B200_SYNCBN", "0") == "1" and world > 1
                                   else "local per-rank batch statistics"), "wall_s": wall},
                 "clocks": clocks,
