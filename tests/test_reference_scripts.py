@@ -96,3 +96,13 @@ def test_unchanged_train_and_test_py_through_the_launcher(tmp_path):
     rows = _losses(os.path.join(exp, "test_unseen_motions.txt"))
     assert len(rows) == 2 and all(0 <= l < 1 for _, _, l in rows)
     assert " - l2: " in open(os.path.join(exp, "test_unseen_motions.txt")).read()
+    # run.py (batch inference caller, run.py:119-141) with the arbitrary-pose model: test_on_batch_with_arbitrary, i.e. the
+    # encode-once inference path, through the third unchanged script (randomly initialised weights: weight_file None)
+    import yaml
+    cfg_path_a, cfg_a = make_dataset.write(str(tmp_path / "arb"), model_type="arbitrary")
+    cfg_a["test"]["weight_file"] = None
+    with open(cfg_path_a, "w") as f:
+        yaml.safe_dump(cfg_a, f)
+    res = _run(["-m", "nsdp_b200.launch", os.path.join(REF, "run.py"), cfg_path_a, "--num_workers", "0"], cuda=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert "Loaded 2 test deformation pairs" in res.stdout and res.stdout.count("Interactive Editing") == 2
