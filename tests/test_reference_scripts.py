@@ -106,3 +106,39 @@ def test_unchanged_train_and_test_py_through_the_launcher(tmp_path):
     res = _run(["-m", "nsdp_b200.launch", os.path.join(REF, "run.py"), cfg_path_a, "--num_workers", "0"], cuda=True)
     assert res.returncode == 0, res.stderr[-3000:]
     assert "Loaded 2 test deformation pairs" in res.stdout and res.stdout.count("Interactive Editing") == 2
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_unchanged_train_py_data_parallel_under_torchrun(tmp_path):
+    """SURVEY 8e design (A): `torchrun -m nsdp_b200.launch train.py cfg` — every rank runs the UNCHANGED script on its own GPU
+    (CUDA_VISIBLE_DEVICES), with its own seed and, for ranks > 0, its own output directory; build_model joins the NCCL job and
+    train_on_batch all-reduces the gradients. The replicas must end with IDENTICAL weights, and a second invocation must
+    resume every rank from rank 0's checkpoint."""
+    from helpers import make_dataset
+    cfg_path, cfg = make_dataset.write(str(tmp_path / "dp"))
+    out = cfg["experiment"]["out_dir"]
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([SHIMS, ROOT, env.get("PYTHONPATH", "")])
+    env["WANDB_MODE"] = "disabled"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29655", "-m", "nsdp_b200.launch", os.path.join(REF, "train.py"), cfg_path, "--num_workers", "0"]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=REF)
+    assert res.returncode == 0, res.stderr[-3000:]
+    r0 = torch.load(os.path.join(out, "harness", "model_00001"), map_location="cpu")
+    r1 = torch.load(os.path.join(out, "rank1", "harness", "model_00001"), map_location="cpu")
+    assert list(r0) == list(r1)
+    for k in r0:
+        if "running_" in k or "num_batches" in k:
+            continue                      # BatchNorm statistics are local per rank by default (what DDP gives the reference)
+        assert torch.equal(r0[k], r1[k]), k
+    assert not torch.equal(r0["encoder.transformer_begin.bn.running_mean"], r1["encoder.transformer_begin.bn.running_mean"])
+    l0 = _losses(os.path.join(out, "harness", "stats.txt"))
+    l1 = _losses(os.path.join(out, "rank1", "harness", "stats.txt"))
+    assert len(l0) == len(l1) == 6 and l0[0][2] != l1[0][2]          # different seeds -> different batches per rank
+    # resume: every rank picks rank 0's newest checkpoint (links in the rank's own directory) and has nothing left to train
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=REF)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert res.stdout.count("Loading model checkpoint from") >= 2
+    assert os.path.islink(os.path.join(out, "rank1", "harness", "model_00001"))
