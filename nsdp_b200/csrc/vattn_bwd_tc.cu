@@ -22,6 +22,11 @@
 #include "stage_f16.cuh"
 #include "vattn_tc_common.cuh"
 
+// d_wd0 / d_bd0 of the decoder attention backward by the tensor core (1) or by the fp32 scratch transposition of round 1 (0)
+#ifndef NSDP_DWD0_MMA
+#define NSDP_DWD0_MMA 1
+#endif
+
 namespace nsdp {
 namespace vtc {
 
@@ -701,6 +706,9 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
       uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
+#if NSDP_DWD0_MMA
+      bool first_tile = true;
+#endif
       auto wait_operand = [&]() {
         mbar_wait_poll(a_ready, ready_phase, err);
         ready_phase ^= 1;
@@ -770,6 +778,31 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           TR(102 + 10 * gi);
           if (elect_one()) mma_commit(acc_done);
         }
+#if NSDP_DWD0_MMA
+        // ---- d_wd0 / d_bd0 += dpre^T [rel | 1]: the A buffer holds dpre (hi / lo), the first 8 KB of the E buffer the
+        //      [128 x 16] operand (rx, ry, rz, 1, 0 ...) of the rows. Transposed product (both operands MN-major, as in
+        //      dw_tc.cu): M = channel, K = the tile's 128 rows, N = 16. Two M-tiles accumulate over ALL tiles of this CTA
+        //      in the spare TMEM columns next to acc0 / acc1.
+        wait_operand();
+        if (elect_one()) {
+          const uint32_t idesc_t = idesc_bf16_mn(128, 16);
+          const uint64_t dh0 = smem_desc(smem_u32(A_hi), 128, 2048), dl0 = smem_desc(smem_u32(A_lo), 128, 2048);
+          const uint64_t rh0 = smem_desc(smem_u32(E), 128, 2048), rl0 = smem_desc(smem_u32(E + 4096), 128, 2048);
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t d = tmem_base + (j ? C::ACC1_COL + C::DP : C::DP);
+            for (int ks = 0; ks < 8; ++ks) {     // 16 rows per k-step = two core matrices = 256 bytes along K
+              const uint64_t xh = dh0 + (uint64_t)j * (32768 >> 4) + (uint64_t)ks * (256 >> 4);
+              const uint64_t xl = dl0 + (uint64_t)j * (32768 >> 4) + (uint64_t)ks * (256 >> 4);
+              const uint64_t yh = rh0 + (uint64_t)ks * (256 >> 4), yl = rl0 + (uint64_t)ks * (256 >> 4);
+              mma_bf16(d, xh, yh, idesc_t, !(first_tile && ks == 0));
+              mma_bf16(d, xl, yh, idesc_t, true);
+              mma_bf16(d, xh, yl, idesc_t, true);
+            }
+          }
+          mma_commit(acc_done);
+        }
+        first_tile = false;
+#endif
       }
     }
   } else {
@@ -832,8 +865,13 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
     };
 
     RowInfoPB ri = row_info_pb<C>(a, tile_begin + blockIdx.x, r, krows, tpb);
+    bool any_tile = false;
     for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
       TW(200);
+#if NSDP_DWD0_MMA
+      if (any_tile) wait_acc();     // the previous tile's d_wd0 product has read dpre (A) and the rel operand (E)
+#endif
+      any_tile = true;
       const size_t tl = (size_t)(tile - tile_begin);
       const bool row_on = ri.c >= 0;
       const int b = (int)(tile / tpb);
@@ -1006,9 +1044,52 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       }
       publish();
       TW(210);
-      // ---- dpre = dh * [h > 0]; d rel; dpre -> fp32 scratch (aliases A, free once GEMM4b is done) ------------------------------
+      // ---- dpre = dh * [h > 0]; d rel ----------------------------------------------------------------------------------------
       wait_acc();
       TW(211);
+#if NSDP_DWD0_MMA
+      {
+        // dpre becomes one more operand (A buffer, GEMM4b is done with it) and the tensor core forms d_wd0 / d_bd0 from it:
+        // no fp32 scratch transposition, no column-owner pass, no block barriers
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            float dh[8], dp[8];
+            tmem_ld8(trow + C::ACC1_COL + ch * 8, dh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w0 = wd0s[ch * 8 + j];
+              const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+              dp[j] = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
+              sx = fmaf(dp[j], w0.x, sx); sy = fmaf(dp[j], w0.y, sy); sz = fmaf(dp[j], w0.z, sz);
+            }
+            uint4 hi, lo;
+            emit(dp, ch, true, nullptr, hi, lo);
+          }
+        }
+        relacc[(part * 3 + 0) * 128 + r] = sx;
+        relacc[(part * 3 + 1) * 128 + r] = sy;
+        relacc[(part * 3 + 2) * 128 + r] = sz;
+        if (part == 0) {
+          // row r of the [128 x 16] operand (rx, ry, rz, 1, 0, ...), MN-major: n-chunk 0 at (r/8)*128 + (r%8)*16, chunk 1 (all
+          // zero) 2048 bytes further; hi image at E, lo image at E + 4096
+          const float x[8] = {ri.rx, ri.ry, ri.rz, 1.f, 0.f, 0.f, 0.f, 0.f};
+          uint4 hi, lo;
+          split2(x[0], x[1], hi.x, lo.x);
+          split2(x[2], x[3], hi.y, lo.y);
+          hi.z = hi.w = lo.z = lo.w = 0u;
+          *reinterpret_cast<uint4 *>(E + a_base) = hi;
+          *reinterpret_cast<uint4 *>(E + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(E + 4096 + a_base) = lo;
+          *reinterpret_cast<uint4 *>(E + 4096 + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      publish();
+      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");     // relacc of every column part is in place
+      TW(212);
+#else
       {
         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
@@ -1044,6 +1125,7 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
         }
       }
+#endif
       if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {   // row owners: d_xyz
         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
@@ -1065,12 +1147,34 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       TW(213);
       ri = nxt;
     }
+#if NSDP_DWD0_MMA
+    if (any_tile) {
+      wait_acc();                      // the last tile's d_wd0 product
+      if (part == 0) {                 // one warp per TMEM lane quarter: lane = channel m (M-tile 0) / 128 + m (M-tile 1)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v[8];
+          tmem_ld8(trow + (j ? C::ACC1_COL + C::DP : C::DP), v);
+          const int m = j * 128 + r;
+          if (m < D) {
+            if (g.d_wd0) {
+              atomicAdd(g.d_wd0 + m * 3 + 0, v[0]); atomicAdd(g.d_wd0 + m * 3 + 1, v[1]); atomicAdd(g.d_wd0 + m * 3 + 2, v[2]);
+            }
+            if (g.d_bd0) atomicAdd(g.d_bd0 + m, v[3]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    (void)cw0; (void)cw1; (void)cw2; (void)cb;
+#else
     if (wtid < D) {
       if (g.d_wd0) {
         atomicAdd(g.d_wd0 + wtid * 3 + 0, cw0); atomicAdd(g.d_wd0 + wtid * 3 + 1, cw1); atomicAdd(g.d_wd0 + wtid * 3 + 2, cw2);
       }
       if (g.d_bd0) atomicAdd(g.d_bd0 + wtid, cb);
     }
+#endif
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
