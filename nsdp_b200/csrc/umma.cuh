@@ -240,6 +240,21 @@ __device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// several loads in flight, ONE wait: tmem_ld8_nowait(...) x n, then tmem_ld_wait() before the registers are read
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// Scheduling fence for registers: the compiler may not move uses of r[] above this point (asm volatile statements keep
+// their order), so a fully unrolled "produce chunk, hand it over" loop is not turned into "all the math, then all the
+// hand-overs".
+__device__ __forceinline__ void pin8(uint32_t (&r)[8]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- fp32 -> (hi, lo) bf16 split, two values packed per 32-bit word (low half = first element) ----------------------------
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);

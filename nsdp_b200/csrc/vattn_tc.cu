@@ -428,7 +428,18 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
 vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed,
                     const unsigned char *__restrict__ tables, float *__restrict__ out, float *__restrict__ stats,
-                    unsigned char *__restrict__ saved, int tpb, long long tiles, int *err) {
+                    unsigned char *__restrict__ saved, int tpb, long long tiles, int *err,
+                    unsigned long long *trace) {
+  // Schedule of one tile t (the tensor pipe trails the workers column chunk by column chunk, and the s-half of the NEXT
+  // tile's GEMM1 runs underneath this tile's softmax epilogue):
+  //   workers                                              tensor
+  //   gp = acc0 -> registers, release acc0                 .
+  //   G = relu(gp + pc) -> A, k-step by k-step             GEMM2 (acc0 = G Wg2^T), starts on the first finished k-step
+  //   s = acc1 -> registers, release acc1                  .
+  //   E(t+1), H(t+1) -> E buffer / A, k-step by k-step     GEMM1b(t+1) (acc1 = H Wd2^T + E T2)
+  //   softmax over the centre's rows of a = acc0; out      GEMM1b(t+1) continues
+  //   release acc0                                         GEMM1a(t+1) (acc0 = H W'^T + E T1)
+  // G overwrites H in place, so epilogue 1 must wait for BOTH halves of GEMM1: the s-half goes first.
   static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *A_hi = smem + C::OFF_A;
@@ -439,8 +450,12 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   float *pcs = reinterpret_cast<float *>(smem + C::OFF_PC);
   float *vcs = reinterpret_cast<float *>(smem + C::OFF_VC);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+  // kready[ks]: the 16 operand columns of k-step ks are in place (8 warps: 2 chunks x 4 lane quarters); e_ready: the
+  // one-hot operand; free0 / free1: every worker is done reading acc0 / acc1, the next GEMM into it may start
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *acc_done = bars + 2 * C::SLOTS, *kready = acc_done + 1;
+  uint64_t *e_ready = kready + C::KSTEPS, *free0 = e_ready + 1, *free1 = free0 + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(free1 + 1);
+  static_assert((2 * C::SLOTS + C::KSTEPS + 4) * 8 + 4 <= 256, "mbarrier area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = a.D;
@@ -463,7 +478,10 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_ready, C::WORKER_WARPS);
+    for (int ks = 0; ks < C::KSTEPS; ++ks) mbar_init(&kready[ks], 8);
+    mbar_init(e_ready, C::WORKER_WARPS);
+    mbar_init(free0, C::WORKER_WARPS);
+    mbar_init(free1, C::WORKER_WARPS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -472,15 +490,15 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr int W1 = 2 * C::KSTEPS;     // slots of GEMM1's weight part
-  constexpr int T1 = 2 * C::E_KSTEPS;   // slots of GEMM1's table part
+  constexpr int KS = C::KSTEPS, ES = C::E_KSTEPS;
+  constexpr int PER_TILE = 3 * KS + 2 * ES;   // slots: Wd2, T2, W', T1, Wg2
 
   if (warp == 0) {
     // ===================== producer: weights + this shape's tables, one slot at a time =====================
     // PL lanes share the work (lane l serves slots l, l + PL, ...): a single thread sustains only about one bulk copy
-    // per ~500 cycles (serial wait / expect_tx / issue chain), less than the tensor pipe consumes
+    // per ~500 cycles (serial wait / expect_tx / issue chain), less than the tensor pipe consumes.
+    // Packed images: GEMM1 region slot 2 ks + m (m = 0: W', 1: Wd2), tables slot 2 ks + m (0: T1, 1: T2), then Wg2.
     constexpr int PL = C::SLOTS / 2;
-    constexpr int PER_TILE = W1 + T1 + C::KSTEPS;
     if (lane < PL) {
       const long long my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
       const long long total = my_tiles * PER_TILE;
@@ -488,9 +506,12 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
         const long long tile = blockIdx.x + (it / PER_TILE) * gridDim.x;
         const int j = (int)(it % PER_TILE);
         const unsigned char *tb = tables + (size_t)(tile / tpb) * table_bytes_per_shape<C>();
-        const unsigned char *src = j < W1 ? packed + (size_t)j * C::SLOT_BYTES
-                                          : (j < W1 + T1 ? tb + (size_t)(j - W1) * C::SLOT_BYTES
-                                                         : packed + (size_t)(j - T1) * C::SLOT_BYTES);
+        const unsigned char *src;
+        if (j < KS) src = packed + (size_t)(2 * j + 1) * C::SLOT_BYTES;                                // Wd2
+        else if (j < KS + ES) src = tb + (size_t)(2 * (j - KS) + 1) * C::SLOT_BYTES;                   // T2
+        else if (j < 2 * KS + ES) src = packed + (size_t)(2 * (j - KS - ES)) * C::SLOT_BYTES;          // W'
+        else if (j < 2 * KS + 2 * ES) src = tb + (size_t)(2 * (j - 2 * KS - ES)) * C::SLOT_BYTES;      // T1
+        else src = packed + (size_t)(2 * KS + (j - 2 * KS - 2 * ES)) * C::SLOT_BYTES;                  // Wg2
         const int s = (int)(it % C::SLOTS);
         const uint32_t ph = (uint32_t)(it / C::SLOTS) & 1;
         mbar_wait(&empty[s], ph ^ 1, err);
@@ -510,10 +531,14 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
       const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
       const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
-      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
-      auto wait_operand = [&]() {
-        mbar_wait_poll(a_ready, ready_phase, err);
-        ready_phase ^= 1;
+      uint32_t slot = 0, slot_phase = 0, kphase = 0, ephase = 0, f0phase = 0, f1phase = 0;
+      auto wait_kstep = [&](int ks) {
+        mbar_wait_poll(&kready[ks], kphase, err);
+        tc_fence_after();
+      };
+      auto wait_bar = [&](uint64_t *bar, uint32_t &phase) {
+        mbar_wait_poll(bar, phase, err);
+        phase ^= 1;
         tc_fence_after();
       };
       auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
@@ -523,51 +548,58 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
         release = &empty[slot];
         if (++slot == C::SLOTS) { slot = 0; slot_phase ^= 1; }
       };
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        wait_operand();
-        for (int ks = 0; ks < C::KSTEPS; ++ks) {
-          const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            uint64_t bh, *rel;
-            take_slot(bh, rel);
-            if (elect_one()) {
-              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
-              mma_bf16(d, ah, bh, idesc, ks > 0);
-              mma_bf16(d, al, bh, idesc, true);
-              mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
-              mma_commit(rel);
-            }
-          }
-        }
-        for (int ks = 0; ks < C::E_KSTEPS; ++ks) {
-          const uint64_t eh = eh0 + ks * A_STEP;
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            uint64_t bh, *rel;
-            take_slot(bh, rel);
-            if (elect_one()) {
-              const uint32_t d = tmem_base + (m ? C::ACC1_COL : 0);
-              mma_bf16(d, eh, bh, idesc, true);
-              mma_bf16(d, eh, bh + (C::SLAB >> 4), idesc, true);
-              mma_commit(rel);
-            }
-          }
-        }
-        if (elect_one()) mma_commit(acc_done);
-        wait_operand();
-        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+      // d (+)= [A operand] * slab^T over all k-steps, three bf16 terms; `follow`: the operand is still being written
+      auto gemm_a = [&](uint32_t d, bool follow) {
+        for (int ks = 0; ks < KS; ++ks) {
           uint64_t bh, *rel;
+          if (follow) wait_kstep(ks);
           take_slot(bh, rel);
           if (elect_one()) {
             const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
-            mma_bf16(tmem_base, ah, bh, idesc, ks > 0);
-            mma_bf16(tmem_base, al, bh, idesc, true);
-            mma_bf16(tmem_base, ah, bh + (C::SLAB >> 4), idesc, true);
+            mma_bf16(d, ah, bh, idesc, ks > 0);
+            mma_bf16(d, al, bh, idesc, true);
+            mma_bf16(d, ah, bh + (C::SLAB >> 4), idesc, true);
             mma_commit(rel);
           }
         }
+      };
+      // d += E * table^T (E is exact in bf16: two terms)
+      auto gemm_e = [&](uint32_t d) {
+        for (int ks = 0; ks < ES; ++ks) {
+          uint64_t bh, *rel;
+          take_slot(bh, rel);
+          if (elect_one()) {
+            const uint64_t eh = eh0 + ks * A_STEP;
+            mma_bf16(d, eh, bh, idesc, true);
+            mma_bf16(d, eh, bh + (C::SLAB >> 4), idesc, true);
+            mma_commit(rel);
+          }
+        }
+      };
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        // ---- GEMM1b: acc1 = H Wd2^T + E T2 (trails the workers writing H) ----
+        TR(100);
+        wait_bar(free1, f1phase);
+        TR(101);
+        gemm_a(tmem_base + C::ACC1_COL, true);
+        kphase ^= 1;
+        wait_bar(e_ready, ephase);
+        gemm_e(tmem_base + C::ACC1_COL);
+        // ---- GEMM1a: acc0 = H W'^T + E T1 ----
+        TR(102);
+        wait_bar(free0, f0phase);
+        TR(103);
+        gemm_a(tmem_base, false);
+        gemm_e(tmem_base);
         if (elect_one()) mma_commit(acc_done);
+        // ---- GEMM2: acc0 = G Wg2^T (trails the workers writing G) ----
+        TR(110);
+        wait_bar(free0, f0phase);
+        TR(111);
+        gemm_a(tmem_base, true);
+        if (elect_one()) mma_commit(acc_done);
+        TR(113);
+        kphase ^= 1;
       }
     }
   } else {
@@ -586,10 +618,41 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
     const size_t sv_st = (size_t)(r >> 4) * (size_t)(2 * C::DP * 32) + (size_t)(r & 15) * 16;   // + chunk * 256 (staged layout)
     const size_t sv_f32 = (size_t)r * 32;                                                       // + chunk * 4096 (fp32 blocks)
 
-    RowInfoPB ri = row_info_pb<C>(a, blockIdx.x, r, krows, tpb);
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const bool row_on = ri.c >= 0;
-      // ---- operands H (bf16 hi/lo) and E (one-hot) -------------------------------------------------------------
+    // chunk ch of the A operand (8 columns of this warp's 32 rows) is written: one arrival on its k-step's barrier
+    auto chunk_done = [&](int ch) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&kready[ch >> 1]);
+    };
+    auto release = [&](uint64_t *bar) {     // this warp's TMEM reads of an accumulator are complete
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+#ifdef NSDP_TRACE
+    const bool tr_on = (tid == 64);
+#define TWF(id) do { if (tr_on) TR(id); } while (0)
+#else
+#define TWF(id) do { } while (0)
+#endif
+    // operands E (one-hot) and H (bf16 hi/lo) of one tile; GEMM1b starts on the first finished k-step
+    auto gen_operands = [&](const RowInfoPB &ri, long long tile) {
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::E_COLS / 8) {
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if ((ri.j >> 3) == ch) {   // ri.j = -1 on inactive rows: never matches
+            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+            const int w = (ri.j & 7) >> 1;
+            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(E + canon_off(128, r, ch * 8)) = e;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e_ready);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int ch = part + q * C::NPART;
@@ -615,70 +678,88 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
             *reinterpret_cast<uint4 *>(p) = hi;
             *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
           }
+          chunk_done(ch);
         }
       }
-#pragma unroll
-      for (int q = 0; q < NE; ++q) {
-        const int ch = part + q * C::NPART;
-        if (ch < C::E_COLS / 8) {
-          uint4 e = make_uint4(0u, 0u, 0u, 0u);
-          if ((ri.j >> 3) == ch) {   // ri.j = -1 on inactive rows: never matches
-            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
-            const int w = (ri.j & 7) >> 1;
-            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
-          }
-          *reinterpret_cast<uint4 *>(E + canon_off(128, r, ch * 8)) = e;
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+    };
 
+    release(free0);                // nothing to protect before the first tile's GEMMs
+    release(free1);
+    RowInfoPB ri = row_info_pb<C>(a, blockIdx.x, r, krows, tpb);
+    if ((long long)blockIdx.x < tiles) gen_operands(ri, blockIdx.x);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const bool row_on = ri.c >= 0;
+      TWF(200);
       // ---- epilogue 1: G = relu(acc0 + pc) -> A operand ------------------------------------------------------------
+      //      acc0 moves to registers first, so GEMM2 (which overwrites it) can start while G is still being produced
       mbar_wait(acc_done, done_phase, err);
       done_phase ^= 1;
       tc_fence_after();
+      TWF(202);
+      {
+        uint32_t gp[NQ][8];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) tmem_ld8_nowait(trow + ch * 8, gp[q]);
+        }
+        tmem_ld_wait();
+        release(free0);
+        TWF(203);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            const int k0 = ch * 8;
+            float g[8];
+            pin8(gp[q]);     // keeps this round's arithmetic behind the previous round's hand-over
+            const float4 p0 = *reinterpret_cast<const float4 *>(pcs + k0), p1 = *reinterpret_cast<const float4 *>(pcs + k0 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            // no masking needed: padded columns have zero weights and pc = 0 (G = 0), inactive rows only feed their own
+            // (ignored) rows of GEMM2
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaxf(__uint_as_float(gp[q][j]) + pv[j], 0.f);
+            uint4 hi, lo;
+            split2(g[0], g[1], hi.x, lo.x);
+            split2(g[2], g[3], hi.y, lo.y);
+            split2(g[4], g[5], hi.z, lo.z);
+            split2(g[6], g[7], hi.w, lo.w);
+            const uint32_t off = canon_off(128, r, k0);
+            *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+            if (saved) {
+              unsigned char *p = saved + (size_t)(tiles + tile) * TB + sv_st + (size_t)ch * 256;
+              *reinterpret_cast<uint4 *>(p) = hi;
+              *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+            }
+            chunk_done(ch);
+          }
+        }
+      }
+      TWF(204);
+      // ---- while GEMM2 runs: the next tile's row description (index + coordinates: two dependent L2 reads) --------
+      const long long ci_grp = __shfl_sync(0xffffffffu, ri.c, lane & ~7);   // row 0 of the group: the centre (or -1)
+      const bool has_next = tile + gridDim.x < tiles;
+      const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
+
+      // ---- GEMM2 done: s = acc1 -> registers (acc1 is free for the next tile's GEMM1b), then the next tile's operands
+      TWF(205);
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+      TWF(206);
+      uint32_t sreg[NQ][8];
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int ch = part + q * C::NPART;
-        if (ch < C::CHUNKS) {
-          const int k0 = ch * 8;
-          float v[8], g[8];
-          tmem_ld8(trow + k0, v);
-          const float4 p0 = *reinterpret_cast<const float4 *>(pcs + k0), p1 = *reinterpret_cast<const float4 *>(pcs + k0 + 4);
-          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-          // no masking needed: padded columns have zero weights and pc = 0 (G = 0), inactive rows only feed their own
-          // (ignored) rows of GEMM2
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = fmaxf(v[j] + pv[j], 0.f);
-          uint4 hi, lo;
-          split2(g[0], g[1], hi.x, lo.x);
-          split2(g[2], g[3], hi.y, lo.y);
-          split2(g[4], g[5], hi.z, lo.z);
-          split2(g[6], g[7], hi.w, lo.w);
-          const uint32_t off = canon_off(128, r, k0);
-          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
-          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
-          if (saved) {
-            unsigned char *p = saved + (size_t)(tiles + tile) * TB + sv_st + (size_t)ch * 256;
-            *reinterpret_cast<uint4 *>(p) = hi;
-            *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
-          }
-        }
+        if (ch < C::CHUNKS) tmem_ld8_nowait(trow + C::ACC1_COL + ch * 8, sreg[q]);
       }
-      tc_fence_before();
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
-
-      // ---- while GEMM2 runs: the next tile's row description (index + coordinates: two dependent L2 reads) --------
-      const long long ci_grp = __shfl_sync(0xffffffffu, ri.c, lane & ~7);   // row 0 of the group: the centre (or -1)
-      const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
+      tmem_ld_wait();
+      release(free1);
+      if (has_next) gen_operands(nxt, tile + gridDim.x);
+      TWF(208);
 
       // ---- epilogue 2: softmax over the 8 rows of a centre; out = sum w * (acc1 + vc) -------------------------------------
-      mbar_wait(acc_done, done_phase, err);
-      done_phase ^= 1;
-      tc_fence_after();
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int ch = part + q * C::NPART;
@@ -686,7 +767,8 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           const int k0 = ch * 8;
           float av[8], sv[8];
           tmem_ld8(trow + k0, av);
-          tmem_ld8(trow + C::ACC1_COL + k0, sv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv[j] = __uint_as_float(sreg[q][j]);
           if (saved) {
             float4 *pa = reinterpret_cast<float4 *>(saved + (size_t)(2 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
             float4 *ps = reinterpret_cast<float4 *>(saved + (size_t)(3 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
@@ -720,7 +802,8 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
           }
         }
       }
-      tc_fence_before();
+      TWF(207);
+      release(free0);              // acc0 is consumed: the next tile's GEMM1a may overwrite it
       ri = nxt;
     }
   }
@@ -751,7 +834,11 @@ static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *w
   if (e != cudaSuccess) return cuda_rc(e);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   unsigned char *saved = (stats && a.saved && a.saved_bytes >= saved_bytes_total<C>(tiles)) ? (unsigned char *)a.saved : nullptr;
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, saved, tpb, tiles, err);
+  unsigned long long *trace = nullptr;
+#ifdef NSDP_TRACE
+  if (const char *tp = getenv("NSDP_TRACE_FWD_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
+#endif
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, saved, tpb, tiles, err, trace);
   return check_launch();
 }
 
