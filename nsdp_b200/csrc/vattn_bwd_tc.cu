@@ -625,16 +625,19 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
   unsigned char *A_hi = smem + L::OFF_A;
   unsigned char *A_lo = A_hi + C::A_HALF;
   unsigned char *E = smem + L::OFF_E;
-  float *scratch = reinterpret_cast<float *>(smem + L::OFF_A);  // aliases A once GEMM4b has consumed it
   unsigned char *stage0 = smem + L::OFF_STAGE;
   float4 *wd0s = reinterpret_cast<float4 *>(smem + L::OFF_WD0);
   float *pcs = reinterpret_cast<float *>(smem + L::OFF_PC);
   float *vcs = reinterpret_cast<float *>(smem + L::OFF_VC);
-  float4 *rels = reinterpret_cast<float4 *>(smem + L::OFF_RELS);
   float *relacc = reinterpret_cast<float *>(smem + L::OFF_RELACC);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + C::SLOTS, *a_ready = bars + 2 * C::SLOTS, *acc_done = a_ready + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+  // kready[ks]: the 16 operand columns of k-step ks are in place (8 warps: 2 chunks x 4 lane quarters); e_ready: the
+  // one-hot operand (GEMM1) / the [rel | 1] operand (d_wd0 product); acc_free: every worker is done reading the
+  // accumulator the next GEMM overwrites. The GEMMs trail the workers' epilogues k-step by k-step (vattn_fwd_oh_kernel).
+  uint64_t *full = bars, *empty = bars + C::SLOTS, *acc_done = bars + 2 * C::SLOTS, *kready = acc_done + 1;
+  uint64_t *e_ready = kready + C::KSTEPS, *acc_free = e_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_free + 1);
+  static_assert((2 * C::SLOTS + C::KSTEPS + 3) * 8 + 4 <= 256, "mbarrier area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = a.D;
@@ -658,7 +661,9 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_ready, C::WORKER_WARPS);
+    for (int ks = 0; ks < C::KSTEPS; ++ks) mbar_init(&kready[ks], 8);
+    mbar_init(e_ready, C::WORKER_WARPS);
+    mbar_init(acc_free, C::WORKER_WARPS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -705,13 +710,15 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
       const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
       const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
-      uint32_t slot = 0, slot_phase = 0, ready_phase = 0;
-#if NSDP_DWD0_MMA
+      uint32_t slot = 0, slot_phase = 0, kphase = 0, ephase = 0, fphase = 0;
       bool first_tile = true;
-#endif
-      auto wait_operand = [&]() {
-        mbar_wait_poll(a_ready, ready_phase, err);
-        ready_phase ^= 1;
+      auto wait_kstep = [&](int ks) {
+        mbar_wait_poll(&kready[ks], kphase, err);
+        tc_fence_after();
+      };
+      auto wait_bar = [&](uint64_t *bar, uint32_t &phase) {
+        mbar_wait_poll(bar, phase, err);
+        phase ^= 1;
         tc_fence_after();
       };
       // waits for the next slot of the ring; returns the B descriptor of its hi slab (lo slab = + SLAB / 16)
@@ -725,10 +732,11 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         // ---- GEMM1: [H | E] -> acc0 (W', T1), acc1 (Wd2, T2) ----
         TR(100);
-        wait_operand();
+        wait_bar(acc_free, fphase);
         TR(101);
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
           const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+          wait_kstep(ks);
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             uint64_t bh, *rel;
@@ -742,6 +750,8 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             }
           }
         }
+        kphase ^= 1;
+        wait_bar(e_ready, ephase);
         for (int ks = 0; ks < C::E_KSTEPS; ++ks) {
           const uint64_t eh = eh0 + ks * A_STEP;
 #pragma unroll
@@ -761,11 +771,12 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
         // ---- GEMM2 (-> acc0), GEMM3 (-> acc0), GEMM4a (-> acc1), GEMM4b (acc1 +=) ----
         for (int gi = 1; gi < 5; ++gi) {
           TR(100 + 10 * gi);
-          wait_operand();
+          wait_bar(acc_free, fphase);
           TR(101 + 10 * gi);
           const uint32_t d = tmem_base + (gi >= 3 ? C::ACC1_COL : 0);
           for (int ks = 0; ks < C::KSTEPS; ++ks) {
             uint64_t bh, *rel;
+            wait_kstep(ks);
             take_slot(bh, rel);
             if (elect_one()) {
               const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
@@ -777,13 +788,15 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           }
           TR(102 + 10 * gi);
           if (elect_one()) mma_commit(acc_done);
+          kphase ^= 1;
         }
-#if NSDP_DWD0_MMA
         // ---- d_wd0 / d_bd0 += dpre^T [rel | 1]: the A buffer holds dpre (hi / lo), the first 8 KB of the E buffer the
         //      [128 x 16] operand (rx, ry, rz, 1, 0 ...) of the rows. Transposed product (both operands MN-major, as in
         //      dw_tc.cu): M = channel, K = the tile's 128 rows, N = 16. Two M-tiles accumulate over ALL tiles of this CTA
         //      in the spare TMEM columns next to acc0 / acc1.
-        wait_operand();
+        for (int ks = 0; ks < C::KSTEPS; ++ks) wait_kstep(ks);     // K runs over the tile's rows here: all of dpre
+        kphase ^= 1;
+        wait_bar(e_ready, ephase);
         if (elect_one()) {
           const uint32_t idesc_t = idesc_bf16_mn(128, 16);
           const uint64_t dh0 = smem_desc(smem_u32(A_hi), 128, 2048), dl0 = smem_desc(smem_u32(A_lo), 128, 2048);
@@ -802,13 +815,11 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           mma_commit(acc_done);
         }
         first_tile = false;
-#endif
       }
     }
   } else {
     // ===================== workers =====================
     const int ww = warp - 2;
-    const int wtid = tid - 64;
     const int quarter = warp & 3;
     const int part = ww >> 2;
     const int r = quarter * 32 + lane;
@@ -828,18 +839,23 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
     const size_t st_row = (size_t)(r >> 4) * (size_t)(slabs * C::DP * 32) + (size_t)(r & 15) * 16;   // + chunk * 256
     const size_t st_tile = (size_t)slabs * 256 * C::DP;
     const size_t ste_row = (size_t)(r >> 4) * (size_t)(C::E_COLS * 32) + (size_t)(r & 15) * 16;
-    float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cb = 0.f;   // d_wd0 / d_bd0 of column wtid, accumulated over all tiles
 
     auto wait_acc = [&]() {
       mbar_wait(acc_done, done_phase, err);
       done_phase ^= 1;
       tc_fence_after();
     };
-    auto publish = [&]() {
-      tc_fence_before();
+    // chunk ch of the A operand (8 columns of this warp's 32 rows) is written: one arrival on its k-step's barrier
+    auto chunk_done = [&](int ch) {
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) mbar_arrive(&kready[ch >> 1]);
+    };
+    // this warp no longer reads the accumulator the next GEMM overwrites (one arrival per GEMM 1 .. 4b)
+    auto release_acc = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
     };
     // x[8] -> bf16 hi/lo words; optional A operand store, optional staged store
     // gradient tiles are staged times gsc (a power of two, 1 unless fp16 staging is on)
@@ -868,31 +884,14 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
     bool any_tile = false;
     for (long long tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
       TW(200);
-#if NSDP_DWD0_MMA
       if (any_tile) wait_acc();     // the previous tile's d_wd0 product has read dpre (A) and the rel operand (E)
-#endif
       any_tile = true;
+      release_acc();                // GEMM1 overwrites acc0 / acc1: the previous tile's readers are all past their loads
       const size_t tl = (size_t)(tile - tile_begin);
       const bool row_on = ri.c >= 0;
       const int b = (int)(tile / tpb);
-      if (part == 0) rels[r] = make_float4(ri.rx, ri.ry, ri.rz, ri.flag);
       unsigned long long gmaskbits = 0ull;
-      // ---- operands H (A + staged) and E (smem + staged) -----------------------------------------------------------
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int ch = part + q * C::NPART;
-        if (ch < C::CHUNKS) {
-          float h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w0 = wd0s[ch * 8 + j];
-            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
-            h[j] = ri.flag * fmaxf(pre, 0.f);
-          }
-          uint4 hi, lo;
-          emit(h, ch, true, stg.h + tl * st_tile, hi, lo);
-        }
-      }
+      // ---- operands E (smem + staged) and H (A + staged); GEMM1 starts on the first finished k-step ---------------------
 #pragma unroll
       for (int q = 0; q < NE; ++q) {
         const int ch = part + q * C::NPART;
@@ -913,104 +912,166 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           *reinterpret_cast<uint4 *>(stg.e + tl * (size_t)(256 * C::E_COLS) + ste_row + (size_t)ch * 256) = e;
         }
       }
-      publish();
-      TW(201);
-      // ---- G = relu(acc0 + pc): operand, staged, mask -------------------------------------------------------------
-      wait_acc();
-      TW(202);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e_ready);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int ch = part + q * C::NPART;
         if (ch < C::CHUNKS) {
-          float v[8], gg[8];
-          tmem_ld8(trow + ch * 8, v);
-          const float4 p0 = *reinterpret_cast<const float4 *>(pcs + ch * 8), p1 = *reinterpret_cast<const float4 *>(pcs + ch * 8 + 4);
-          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          float h[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            gg[j] = fmaxf(v[j] + pv[j], 0.f);
-            if (gg[j] > 0.f) gmaskbits |= 1ull << (q * 8 + j);
+            const float4 w0 = wd0s[ch * 8 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
           }
           uint4 hi, lo;
-          emit(gg, ch, true, stg.g + tl * st_tile, hi, lo);
+          emit(h, ch, true, stg.h + tl * st_tile, hi, lo);
+          chunk_done(ch);
         }
       }
-      publish();
+      TW(201);
+      // ---- G = relu(acc0 + pc): operand, staged, mask. acc0 moves to registers first: GEMM2 overwrites it and starts on
+      //      the first finished k-step ---------------------------------------------------------------------------------------
+      wait_acc();
+      TW(202);
+      {
+        uint32_t gp[NQ][8];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) tmem_ld8_nowait(trow + ch * 8, gp[q]);
+        }
+        tmem_ld_wait();
+        release_acc();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            float gg[8];
+            pin8(gp[q]);     // keeps this round's arithmetic behind the previous round's hand-over
+            const float4 p0 = *reinterpret_cast<const float4 *>(pcs + ch * 8), p1 = *reinterpret_cast<const float4 *>(pcs + ch * 8 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              gg[j] = fmaxf(__uint_as_float(gp[q][j]) + pv[j], 0.f);
+              if (gg[j] > 0.f) gmaskbits |= 1ull << (q * 8 + j);
+            }
+            uint4 hi, lo;
+            emit(gg, ch, true, stg.g + tl * st_tile, hi, lo);
+            chunk_done(ch);
+          }
+        }
+      }
       TW(203);
       // ---- while GEMM2 runs: the next tile's row description -------------------------------------------------------------
       const RowInfoPB nxt = row_info_pb<C>(a, tile + gridDim.x, r, krows, tpb);
       // ---- w = exp(a - max) / sum, s = acc1 + vc; ds = w * dout, da = ds * (s - out) ---------------------------------------
-      //      da -> A operand + staged; ds -> staged + parked (split words) in acc1's columns
+      //      Two passes, so that GEMM3 (which overwrites acc0 = a) can trail the second one: (1) w of every chunk, kept as
+      //      fp32 in the chunk's own 32 bytes of the (free) A buffer, then acc0 is released; (2) da -> A operand (over w) +
+      //      staged, ds -> staged + parked (split words) in acc1's columns.
       {
-        const float *st_mx = stats + (size_t)(row_on ? ri.c : 0) * D;
-        const float *st_iv = stats + ((size_t)BM + (row_on ? ri.c : 0)) * D;
-        const float *p_go = dout + (size_t)(row_on ? ri.c : 0) * D;
-        const float *p_o = out + (size_t)(row_on ? ri.c : 0) * D;
-        float4 cmx, civ, cgo, co;   // inputs of the current half-chunk (loaded one half-chunk ahead)
-        auto load_half = [&](int hc, float4 &mx, float4 &iv, float4 &go, float4 &o) {
-          const int col = (part + (hc >> 1) * C::NPART) * 8 + (hc & 1) * 4;
-          mx = iv = go = o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_on && col < D) {
-            mx = ldg4(st_mx + col); iv = ldg4(st_iv + col); go = ldg4(p_go + col); o = ldg4(p_o + col);
+        const size_t crow = (size_t)(row_on ? ri.c : 0) * D;
+        const float *st_mx = stats + crow;
+        const float *st_iv = stats + (size_t)BM * D + crow;
+        const float *p_go = dout + crow;
+        const float *p_o = out + crow;
+        float4 cmx[2], civ[2];      // inputs of the current chunk (loaded one chunk ahead)
+        auto load_stats = [&](int q, float4 (&mx)[2], float4 (&iv)[2]) {
+          const int col = (part + q * C::NPART) * 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mx[h] = iv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_on && col + h * 4 < D) { mx[h] = ldg4(st_mx + col + h * 4); iv[h] = ldg4(st_iv + col + h * 4); }
           }
         };
-        load_half(0, cmx, civ, cgo, co);
+        load_stats(0, cmx, civ);
         wait_acc();
-      TW(204);
+        TW(204);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const int ch = part + q * C::NPART;
-          float av[8], sv[8], ds[8], da[8];
+          float4 nmx[2], niv[2];
+          load_stats(q + 1, nmx, niv);      // beyond the last chunk: col >= D, nothing is loaded
           if (ch < C::CHUNKS) {
+            float av[8];
             tmem_ld8(trow + ch * 8, av);
-            tmem_ld8(trow + C::ACC1_COL + ch * 8, sv);
-          }
+            const float mxs[8] = {cmx[0].x, cmx[0].y, cmx[0].z, cmx[0].w, cmx[1].x, cmx[1].y, cmx[1].z, cmx[1].w};
+            const float ivs[8] = {civ[0].x, civ[0].y, civ[0].z, civ[0].w, civ[1].x, civ[1].y, civ[1].z, civ[1].w};
+            float w[8];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 nmx, niv, ngo, no;
-            load_half(q * 2 + half + 1, nmx, niv, ngo, no);   // beyond the last chunk: col >= D, nothing is loaded
-            if (ch < C::CHUNKS) {
-              const float4 v0 = *reinterpret_cast<const float4 *>(vcs + ch * 8 + half * 4);
-              const float mxs[4] = {cmx.x, cmx.y, cmx.z, cmx.w}, ivs[4] = {civ.x, civ.y, civ.z, civ.w};
-              const float gos[4] = {cgo.x, cgo.y, cgo.z, cgo.w}, os[4] = {co.x, co.y, co.z, co.w};
-              const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
-              const bool on = row_on && ch * 8 + half * 4 < D;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = half * 4 + u;
-                const float w = on ? __expf(av[j] - mxs[u]) * ivs[u] : 0.f;
-                ds[j] = w * gos[u];
-                da[j] = ds[j] * (sv[j] + vv[u] - os[u]);
-              }
-            }
-            cmx = nmx; civ = niv; cgo = ngo; co = no;
+            for (int j = 0; j < 8; ++j) w[j] = (row_on && ch * 8 + (j & 4) < D) ? __expf(av[j] - mxs[j]) * ivs[j] : 0.f;
+            *reinterpret_cast<float4 *>(A_hi + a_base + ch * 2048) = make_float4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<float4 *>(A_lo + a_base + ch * 2048) = make_float4(w[4], w[5], w[6], w[7]);
           }
+          cmx[0] = nmx[0]; cmx[1] = nmx[1]; civ[0] = niv[0]; civ[1] = niv[1];
+        }
+        release_acc();
+        float4 cgo[2], co[2];
+        auto load_grads = [&](int q, float4 (&go)[2], float4 (&o)[2]) {
+          const int col = (part + q * C::NPART) * 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            go[h] = o[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_on && col + h * 4 < D) { go[h] = ldg4(p_go + col + h * 4); o[h] = ldg4(p_o + col + h * 4); }
+          }
+        };
+        load_grads(0, cgo, co);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          float4 ngo[2], no[2];
+          load_grads(q + 1, ngo, no);
           if (ch < C::CHUNKS) {
+            float sv[8], ds[8], da[8];
+            tmem_ld8(trow + C::ACC1_COL + ch * 8, sv);
+            const float4 w0 = *reinterpret_cast<const float4 *>(A_hi + a_base + ch * 2048);
+            const float4 w1 = *reinterpret_cast<const float4 *>(A_lo + a_base + ch * 2048);
+            const float4 v0 = *reinterpret_cast<const float4 *>(vcs + ch * 8), v1 = *reinterpret_cast<const float4 *>(vcs + ch * 8 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const float gos[8] = {cgo[0].x, cgo[0].y, cgo[0].z, cgo[0].w, cgo[1].x, cgo[1].y, cgo[1].z, cgo[1].w};
+            const float os[8] = {co[0].x, co[0].y, co[0].z, co[0].w, co[1].x, co[1].y, co[1].z, co[1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              ds[j] = w[j] * gos[j];
+              da[j] = ds[j] * (sv[j] + vv[j] - os[j]);
+            }
             uint4 hi, lo;
             emit(da, ch, true, stg.da + tl * st_tile, hi, lo, gsc);
+            chunk_done(ch);
             emit(ds, ch, false, stg.ds + tl * st_tile, hi, lo, gsc);
             const uint32_t pk[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
             tmem_st8(trow + C::ACC1_COL + ch * 8, pk);
           }
+          cgo[0] = ngo[0]; cgo[1] = ngo[1]; co[0] = no[0]; co[1] = no[1];
         }
       }
       tmem_st_wait();
-      publish();
       TW(205);
-      // ---- GEMM3 done: A is free -> operand ds from its parked words (GEMM4a) ---------------------------------------------
+      // ---- GEMM3 done: A is free -> operand ds from its parked words; they leave acc1 first (GEMM4a overwrites it) -----------
       wait_acc();
       TW(206);
+      {
+        uint32_t pk[NQ][8];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int ch = part + q * C::NPART;
-        if (ch < C::CHUNKS) {
-          uint32_t pk[8];
-          tmem_ld8u(trow + C::ACC1_COL + ch * 8, pk);
-          *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) tmem_ld8_nowait(trow + C::ACC1_COL + ch * 8, pk[q]);
+        }
+        tmem_ld_wait();
+        release_acc();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+            *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[q][4], pk[q][5], pk[q][6], pk[q][7]);
+            chunk_done(ch);
+          }
         }
       }
-      publish();
       TW(207);
       // ---- dgp = dg * [g > 0] (reads acc0 while GEMM4a fills acc1): staged + parked in acc0's columns ---------------------------
 #pragma unroll
@@ -1029,9 +1090,10 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       }
       tmem_st_wait();
       TW(208);
-      // ---- GEMM4a done: A is free -> operand dgp (GEMM4b) ----------------------------------------------------------------------
+      // ---- GEMM4a done: A is free -> operand dgp (GEMM4b accumulates into acc1, which nobody reads now) -----------------------
       wait_acc();
       TW(209);
+      release_acc();
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int ch = part + q * C::NPART;
@@ -1040,17 +1102,31 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
           tmem_ld8u(trow + ch * 8, pk);
           *reinterpret_cast<uint4 *>(A_hi + a_base + ch * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4 *>(A_lo + a_base + ch * 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          chunk_done(ch);
         }
       }
-      publish();
       TW(210);
       // ---- dpre = dh * [h > 0]; d rel ----------------------------------------------------------------------------------------
       wait_acc();
       TW(211);
-#if NSDP_DWD0_MMA
       {
-        // dpre becomes one more operand (A buffer, GEMM4b is done with it) and the tensor core forms d_wd0 / d_bd0 from it:
-        // no fp32 scratch transposition, no column-owner pass, no block barriers
+        // dpre becomes one more operand (A buffer, GEMM4b is done with it) and the tensor core forms d_wd0 / d_bd0 from it
+        // (transposed product with the [rel | 1] operand in the E buffer)
+        if (part == 0) {
+          // row r of the [128 x 16] operand (rx, ry, rz, 1, 0, ...), MN-major: n-chunk 0 at (r/8)*128 + (r%8)*16, chunk 1 (all
+          // zero) 2048 bytes further; hi image at E, lo image at E + 4096
+          uint4 hi, lo;
+          split2(ri.rx, ri.ry, hi.x, lo.x);
+          split2(ri.rz, 1.f, hi.y, lo.y);
+          hi.z = hi.w = lo.z = lo.w = 0u;
+          *reinterpret_cast<uint4 *>(E + a_base) = hi;
+          *reinterpret_cast<uint4 *>(E + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(E + 4096 + a_base) = lo;
+          *reinterpret_cast<uint4 *>(E + 4096 + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(e_ready);
         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -1067,65 +1143,16 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
             }
             uint4 hi, lo;
             emit(dp, ch, true, nullptr, hi, lo);
+            chunk_done(ch);
           }
         }
         relacc[(part * 3 + 0) * 128 + r] = sx;
         relacc[(part * 3 + 1) * 128 + r] = sy;
         relacc[(part * 3 + 2) * 128 + r] = sz;
-        if (part == 0) {
-          // row r of the [128 x 16] operand (rx, ry, rz, 1, 0, ...), MN-major: n-chunk 0 at (r/8)*128 + (r%8)*16, chunk 1 (all
-          // zero) 2048 bytes further; hi image at E, lo image at E + 4096
-          const float x[8] = {ri.rx, ri.ry, ri.rz, 1.f, 0.f, 0.f, 0.f, 0.f};
-          uint4 hi, lo;
-          split2(x[0], x[1], hi.x, lo.x);
-          split2(x[2], x[3], hi.y, lo.y);
-          hi.z = hi.w = lo.z = lo.w = 0u;
-          *reinterpret_cast<uint4 *>(E + a_base) = hi;
-          *reinterpret_cast<uint4 *>(E + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4 *>(E + 4096 + a_base) = lo;
-          *reinterpret_cast<uint4 *>(E + 4096 + a_base + 2048) = make_uint4(0u, 0u, 0u, 0u);
-        }
       }
-      publish();
+      tc_fence_before();            // this tile's reads of acc1 are ordered before the barrier: the next GEMM1 may overwrite it
       asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");     // relacc of every column part is in place
       TW(212);
-#else
-      {
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int ch = part + q * C::NPART;
-          if (ch < C::CHUNKS) {
-            float dh[8];
-            tmem_ld8(trow + C::ACC1_COL + ch * 8, dh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = ch * 8 + j;
-              const float4 w0 = wd0s[col];
-              const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
-              const float dp = (ri.flag != 0.f && pre > 0.f) ? dh[j] : 0.f;
-              sx = fmaf(dp, w0.x, sx); sy = fmaf(dp, w0.y, sy); sz = fmaf(dp, w0.z, sz);
-              if (col < D) scratch[(size_t)col * L::SCR_LD + ((r + col) & 127)] = dp;
-            }
-          }
-        }
-        relacc[(part * 3 + 0) * 128 + r] = sx;
-        relacc[(part * 3 + 1) * 128 + r] = sy;
-        relacc[(part * 3 + 2) * 128 + r] = sz;
-      }
-      tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(C::WORKER_WARPS * 32) : "memory");
-      TW(212);
-      if (wtid < D) {   // column owners: d_wd0 / d_bd0 partial sums over the 128 rows of the tile
-        const float *colp = scratch + (size_t)wtid * L::SCR_LD;
-#pragma unroll 4
-        for (int rr = 0; rr < 128; ++rr) {
-          const float dp = colp[(rr + wtid) & 127];
-          const float4 rl = rels[rr];
-          cw0 = fmaf(dp, rl.x, cw0); cw1 = fmaf(dp, rl.y, cw1); cw2 = fmaf(dp, rl.z, cw2); cb += dp;
-        }
-      }
-#endif
       if (part == 0 && ri.flag != 0.f && (g.d_xyz_c || g.d_xyz_n)) {   // row owners: d_xyz
         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
@@ -1147,7 +1174,6 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       TW(213);
       ri = nxt;
     }
-#if NSDP_DWD0_MMA
     if (any_tile) {
       wait_acc();                      // the last tile's d_wd0 product
       if (part == 0) {                 // one warp per TMEM lane quarter: lane = channel m (M-tile 0) / 128 + m (M-tile 1)
@@ -1166,15 +1192,6 @@ vattn_bwd_oh_kernel(const nsdp_vattn_args a, const float *__restrict__ out, cons
       }
       tc_fence_before();
     }
-    (void)cw0; (void)cw1; (void)cw2; (void)cb;
-#else
-    if (wtid < D) {
-      if (g.d_wd0) {
-        atomicAdd(g.d_wd0 + wtid * 3 + 0, cw0); atomicAdd(g.d_wd0 + wtid * 3 + 1, cw1); atomicAdd(g.d_wd0 + wtid * 3 + 2, cw2);
-      }
-      if (g.d_bd0) atomicAdd(g.d_bd0 + wtid, cb);
-    }
-#endif
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -1641,7 +1658,7 @@ static int launch_bwd_oh(const nsdp_vattn_args &a, const float *out, const float
     } else {
       unsigned long long *trace = nullptr;
 #ifdef NSDP_TRACE
-      if (const char *tp = getenv("NSDP_TRACE_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
+      if (const char *tp = getenv("NSDP_TRACE_BWD_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
 #endif
       kern<<<grid, C::THREADS, BwdLayout<C>::SMEM, st>>>(a, out, stats, dout, g, packed, tables, stg, tpb, t0, t1, err, trace);
     }
