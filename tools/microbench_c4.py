@@ -40,6 +40,26 @@ def timed(fn, reps=30, warm=5):
     return ts[len(ts) // 2], ts[len(ts) // 10], ts[(9 * len(ts)) // 10]
 
 
+_big = torch.empty(64 << 20, device=DEV)
+
+
+def queued(fn, calls=24, reps=10):
+    """Per-call time with `calls` launches queued behind a long dummy kernel: a single call's event pair also sees the host's
+    launch cost (two launches from Python, ~15 us), which matters for the narrow widths."""
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(4):
+            _big.add_(1.0)
+        a.record()
+        for i in range(calls):
+            fn(i)
+        b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) / calls)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 g = torch.Generator().manual_seed(5)
 xs = [(torch.rand(R, 3, generator=g) - 0.5).to(DEV) for _ in range(NBUF)]
 outs = [torch.empty(R, 3, device=DEV) for _ in range(NBUF)]
@@ -48,6 +68,7 @@ for W in (16, 32, 64, 128, 256):
     w = [torch.from_numpy(t).to(DEV) for t in synth.mlp_weights(W, L, seed=W)]
     net = ops.FusedMLP(*w, impl=0)
     ms, p10, p90 = timed(lambda i: net(xs[i % NBUF], outs[i % NBUF]))
+    ms_q = queued(lambda i: net(xs[i % NBUF], outs[i % NBUF]))
     w_in, b_in, w_h, b_h, w_out, b_out = w
 
     def eager(i):
@@ -94,7 +115,9 @@ for W in (16, 32, 64, 128, 256):
     intensity = flop / 24.0
     ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
     rows.append({
-        "W": W, "rows": R, "layers": L + 2, "ms": ms, "ms_p10": p10, "ms_p90": p90,
+        "W": W, "rows": R, "layers": L + 2, "ms": ms, "ms_p10": p10, "ms_p90": p90, "ms_queued": ms_q,
+        "hbm_gbs_compulsory_queued": R * 24 / (ms_q * 1e-3) / 1e9,
+        "frac_tensor_peak_executed_queued": 3 * R * 2.0 * L * W * W / (ms_q * 1e-3) / 1e12 / peaks["bf16_tflops"],
         "points_per_s": R / (ms * 1e-3), "algorithmic_tflops": tfl, "executed_mma_tflops": 3 * R * 2.0 * L * W * W / (ms * 1e-3) / 1e12,
         "hbm_gbs_compulsory": gbs, "flop_per_byte": intensity, "bound": "hbm" if intensity < ridge else "tensor",
         "frac_hbm_peak": gbs / peaks["hbm_gbs"], "frac_tensor_peak": tfl / peaks["bf16_tflops"],
