@@ -315,6 +315,12 @@ int nsdp_set_stage_format(int fmt);
 int nsdp_selftest_umma(const float *A, const float *B, float *D, int N, int K, int split, int mn, int *err,
                        void *stream);
 
+/* The same product on a CTA PAIR (tcgen05 cta_group::2, a cluster of two CTAs, one MMA stream issued by the leader):
+ * D (256,N) = A (256,K) * B (N,K)^T; CTA c holds rows [128c, 128c+128) of A and rows [N/2 c, N/2 c + N/2) of B.
+ * N % 16 == 0, 32 <= N <= 256, K % 16 == 0. Pins the pair conventions (allocation in both CTAs, M = 256 instruction
+ * descriptor, per-CTA halves of B behind one descriptor, multicast commit) before a kernel relies on them. */
+int nsdp_selftest_umma2(const float *A, const float *B, float *D, int N, int K, int split, int *err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

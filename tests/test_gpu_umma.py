@@ -45,3 +45,26 @@ def test_umma_mn_major_operands(N, K):
     want = X.double().t() @ Y.double()
     rel = ((D.double() - want).norm() / want.norm()).item()
     assert rel < 3e-5, rel
+
+
+def _run_pair(N, K, split, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A, B = torch.randn(256, K, generator=g), torch.randn(N, K, generator=g)
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    D = torch.zeros(256, N, device=DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    rc = _lib.lib().nsdp_selftest_umma2(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split, err.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "nsdp_selftest_umma2")
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "mbarrier wait timed out"
+    return A, B, D.cpu()
+
+
+@pytest.mark.parametrize("N,K", [(32, 16), (128, 64), (208, 128), (256, 128)])
+def test_umma_cta_pair(N, K):
+    """cta_group::2: one M = 256 product across two CTAs (each holds 128 rows of A and half of B's rows)."""
+    A, B, D = _run_pair(N, K, 1, seed=11)
+    want = A.double() @ B.double().t()
+    rel = ((D.double() - want).norm() / want.norm()).item()
+    assert rel < 3e-5, rel

@@ -42,3 +42,12 @@ def fb():
 
 t_fb = timed(fb)
 print(f"{os.environ.get('NSDP_B200_LIB', 'default')}: decoder forward (eval) {t_fwd:.3f} ms, forward + backward {t_fb:.3f} ms")
+if os.environ.get("PROFILE"):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            fb()
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]
+    for e in rows:
+        print(f"  {e.device_time_total / 3e3:8.3f} ms/iter  {e.count // 3:3d} launches  {e.key[:90]}")
