@@ -122,16 +122,6 @@ extern "C" int nsdp_selftest_umma(const float *A, const float *B, float *D, int 
 // ---------------------------------------------------------------------------------------------------------------------
 namespace nsdp {
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 umma2_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int N, int K,
                       int split, int *err) {
@@ -163,11 +153,7 @@ umma2_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, 
   }
   uint32_t ncols = 32;
   while ((int)ncols < N) ncols *= 2;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
+  if (warp == 0) tmem_alloc_pair(&tmem_base_s, ncols);
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
@@ -189,19 +175,11 @@ umma2_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, 
       for (int ks = 0; ks < K / 16; ++ks) {
         const uint64_t ad = smem_desc(smem_u32(pa) + ks * 2 * lbo_a, lbo_a, 128);
         const uint64_t bd = smem_desc(smem_u32(pb) + ks * 2 * lbo_b, lbo_b, 128);
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
-            "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
-            : "memory");
+        mma_bf16_pair(tmem_base, ad, bd, idesc, acc != 0);
         acc = 1;
       }
     }
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(&bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
+    mma_commit_pair(&bar);
   }
   mbar_wait(&bar, 0, err);
   tc_fence_after();
@@ -214,7 +192,7 @@ umma2_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, 
   }
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  if (warp == 0) tmem_dealloc_pair(tmem_base, ncols);
 }
 
 }  // namespace nsdp

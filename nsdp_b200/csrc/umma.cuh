@@ -87,6 +87,23 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// pure polling, always (no suspension: reacts within tens of cycles). For the ONE warp per CTA that sits on a latency-
+// critical relay (CTA-pair kernels: "my half of the slot has landed" -> leader), never for many warps at once.
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity, int *err = nullptr) {
+  if (mbar_test_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0u) {
+      const unsigned long long dt = global_ns() - t0;
+      const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
+      if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
+        if (err) atomicExch(err, 1);
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity, int *err = nullptr) {
 #ifndef NSDP_ISSUER_POLL   // measured on B200: no gain over try_wait (A/B, bench step 38.5 vs 39.4 ms within noise), so off
   mbar_wait(bar, parity, err);
@@ -254,6 +271,87 @@ __device__ __forceinline__ void pin8(uint32_t (&r)[8]) {
   asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// ---- CTA pair (cluster of two CTAs, tcgen05 cta_group::2): conventions pinned by nsdp_selftest_umma2 -------------------
+//   * both CTAs allocate / free TMEM with the cta_group::2 forms and get the same address; CTA c's TMEM holds rows
+//     [128 c, 128 c + 128) of the M = 256 accumulator, all N columns;
+//   * the leader (cluster rank 0) issues the MMAs; ONE descriptor pair addresses the same shared-memory offsets in both
+//     CTAs: each holds its own 128 rows of A and its own N/2 rows of B;
+//   * tcgen05.commit with the multicast mask arrives on the mbarrier at the same offset in BOTH CTAs;
+//   * threads of the peer CTA arrive on the leader's mbarriers through their cluster-space address (mapa), the leader waits
+//     with cluster-scope acquire.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cluster-space address of the same shared-memory location in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release on every
+// hand-over made the pair kernel twice as slow (measured); what the arrival publishes is this CTA's own shared memory
+// (fence.proxy.async before it), read by this CTA's own tensor core
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded like mbar_wait; for barriers that receive arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, int *err = nullptr) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 63u) == 0u) {
+      const unsigned long long dt = global_ns() - t0;
+      const bool flagged = err && *reinterpret_cast<volatile int *>(err) != 0;
+      if (dt > 2000000000ull || (flagged && dt > 20000ull)) {
+        if (err) atomicExch(err, 1);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in BOTH CTAs once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 
 // ---- fp32 -> (hi, lo) bf16 split, two values packed per 32-bit word (low half = first element) ----------------------------
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {

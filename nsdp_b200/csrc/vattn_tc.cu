@@ -40,7 +40,7 @@ constexpr size_t packed_bytes() {
 
 template <class C>
 __global__ void pack_weights_kernel(const float *__restrict__ wpt, const float *__restrict__ wd2t,
-                                    const float *__restrict__ wg2t, int D, unsigned char *__restrict__ out) {
+                                    const float *__restrict__ wg2t, int D, unsigned char *__restrict__ out, int pair = 0) {
   // one thread per (matrix m, n, k-pair)
   const int total = 3 * C::DP * (C::DP / 2);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -54,14 +54,13 @@ __global__ void pack_weights_kernel(const float *__restrict__ wpt, const float *
     uint32_t hi, lo;
     split2(x0, x1, hi, lo);
     const int ks = k >> 4, kin = k & 15;
-    const uint32_t in_slab = canon_off(C::DP, n, kin);
     size_t base;
     if (m < 2)
       base = (size_t)ks * 4 * C::SLAB + (size_t)m * 2 * C::SLAB;
     else
       base = (size_t)C::KSTEPS * 4 * C::SLAB + (size_t)ks * 2 * C::SLAB;
-    *reinterpret_cast<uint32_t *>(out + base + in_slab) = hi;
-    *reinterpret_cast<uint32_t *>(out + base + C::SLAB + in_slab) = lo;
+    *reinterpret_cast<uint32_t *>(out + base + slot_off<C>(n, kin, 0, pair)) = hi;
+    *reinterpret_cast<uint32_t *>(out + base + slot_off<C>(n, kin, 1, pair)) = lo;
   }
 }
 
@@ -811,6 +810,445 @@ vattn_fwd_oh_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ p
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// =====================================================================================================================
+// CTA-PAIR version of the one-hot forward kernel (tcgen05 cta_group::2; conventions: umma.cuh, nsdp_selftest_umma2).
+// Two CTAs on the two SMs of a TPC walk over PAIRS of tiles of the same shape: CTA c owns tile 2 j + c (its own A / E
+// operands, its own 128 TMEM lanes, its own epilogues), the leader (rank 0) issues every MMA as ONE M = 256 instruction.
+// Each CTA streams only ITS HALF of every weight / table slab (rows [104 c, 104 c + 104) of the [208 x 16] slab): half the
+// L2 -> SM weight traffic, half the shared-memory fill and B-operand reads per SM -- the single-CTA kernel is bound by
+// exactly these (44.5 KB of shared-memory traffic per k-step against 312 MMA cycles).
+// Schedule per tile: the one of vattn_fwd_oh_kernel (hand-over per k-step, GEMM1b of the next tile under the softmax
+// epilogue). Barriers live at the same offsets in both CTAs; the workers of BOTH CTAs arrive on the LEADER's kready /
+// e_ready / free barriers (cluster-space address), the MMA completions are multicast to both CTAs' acc_done / empty[],
+// the peer's warp 1 relays "my half of slot s has landed" to the leader's pfull[s].
+// =====================================================================================================================
+template <class C>
+struct PairCfg {
+  static constexpr int NH = C::DP / 2;                 // B rows per CTA
+  static constexpr int HRUN = NH * 16;                 // one 8-wide k chunk of a half slab (contiguous in the packed image)
+  static constexpr int HSLAB = 2 * HRUN;               // [NH x 16] bf16
+  static constexpr int HSLOT = 2 * HSLAB;              // hi + lo
+  static constexpr int SLOTS = 12;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_E = OFF_A + 2 * C::A_HALF;
+  static constexpr int OFF_STAGE = OFF_E + C::E_BYTES;
+  static constexpr int OFF_WD0 = OFF_STAGE + SLOTS * HSLOT;
+  static constexpr int OFF_PC = OFF_WD0 + C::DP * 16;
+  static constexpr int OFF_VC = OFF_PC + C::DP * 4;
+  static constexpr int OFF_BAR = OFF_VC + C::DP * 4;
+  static constexpr int SMEM = OFF_BAR + 512;
+  static_assert(C::DP % 32 == 0 || (C::DP / 2) % 8 == 0, "half slabs are whole core matrices");
+  static_assert((3 * SLOTS + C::KSTEPS + 5) * 8 + 4 <= 512, "mbarrier area");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <class C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::THREADS, 1)
+vattn_fwd_oh2_kernel(const nsdp_vattn_args a, const unsigned char *__restrict__ packed,
+                     const unsigned char *__restrict__ tables, float *__restrict__ out, float *__restrict__ stats,
+                     unsigned char *__restrict__ saved, int tpb, long long tiles, int *err,
+                     unsigned long long *trace) {
+  static_assert(C::OH && C::KR == 8, "one-hot kernel: 8 rows per centre");
+  using P = PairCfg<C>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *A_hi = smem + P::OFF_A;
+  unsigned char *A_lo = A_hi + C::A_HALF;
+  unsigned char *E = smem + P::OFF_E;
+  unsigned char *stage0 = smem + P::OFF_STAGE;
+  float4 *wd0s = reinterpret_cast<float4 *>(smem + P::OFF_WD0);
+  float *pcs = reinterpret_cast<float *>(smem + P::OFF_PC);
+  float *vcs = reinterpret_cast<float *>(smem + P::OFF_VC);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + P::OFF_BAR);
+  uint64_t *full = bars, *empty = full + P::SLOTS, *pfull = empty + P::SLOTS, *acc_done = pfull + P::SLOTS;
+  uint64_t *kready = acc_done + 1, *e_ready = kready + C::KSTEPS, *free0 = e_ready + 1, *free1 = free0 + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(free1 + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int D = a.D;
+  const int krows = a.K + 1;
+  const int tpp = (tpb + 1) / 2;                               // tile pairs per shape
+  const long long pairs = (long long)a.B * tpp;
+  const long long pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
+
+  for (int kk = tid; kk < C::DP; kk += C::THREADS) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = 0.f, v = 0.f;
+    if (kk < D) {
+      w = make_float4(a.wd0[kk * 3 + 0], a.wd0[kk * 3 + 1], a.wd0[kk * 3 + 2], a.bd0[kk]);
+      p = a.pc[kk];
+      v = a.vc[kk];
+    }
+    wd0s[kk] = w;
+    pcs[kk] = p;
+    vcs[kk] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < P::SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
+    }
+    for (int ks = 0; ks < C::KSTEPS; ++ks) mbar_init(&kready[ks], 16);     // 8 warps of each CTA
+    mbar_init(e_ready, 2 * C::WORKER_WARPS);
+    mbar_init(free0, 2 * C::WORKER_WARPS);
+    mbar_init(free1, 2 * C::WORKER_WARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int KS = C::KSTEPS, ES = C::E_KSTEPS;
+  constexpr int PER_TILE = 3 * KS + 2 * ES;   // slots: Wd2, T2, W', T1, Wg2
+
+  if (warp == 0) {
+    // ===================== producer: this CTA's half of every slot =====================
+    constexpr int PL = 6;
+    if (lane < PL) {
+      const long long mine = pair0 < pairs ? (pairs - pair0 + pstride - 1) / pstride : 0;
+      const long long total = mine * PER_TILE;
+      for (long long it = lane; it < total; it += PL) {
+        const long long pr = pair0 + (it / PER_TILE) * pstride;
+        const int j = (int)(it % PER_TILE);
+        const unsigned char *tb = tables + (size_t)(pr / tpp) * table_bytes_per_shape<C>();
+        const unsigned char *src;
+        if (j < KS) src = packed + (size_t)(2 * j + 1) * C::SLOT_BYTES;                                // Wd2
+        else if (j < KS + ES) src = tb + (size_t)(2 * (j - KS) + 1) * C::SLOT_BYTES;                   // T2
+        else if (j < 2 * KS + ES) src = packed + (size_t)(2 * (j - KS - ES)) * C::SLOT_BYTES;          // W'
+        else if (j < 2 * KS + 2 * ES) src = tb + (size_t)(2 * (j - 2 * KS - ES)) * C::SLOT_BYTES;      // T1
+        else src = packed + (size_t)(2 * KS + (j - 2 * KS - 2 * ES)) * C::SLOT_BYTES;                  // Wg2
+        const int s = (int)(it % P::SLOTS);
+        const uint32_t ph = (uint32_t)(it / P::SLOTS) & 1;
+        mbar_wait(&empty[s], ph ^ 1, err);
+        mbar_arrive_expect_tx(&full[s], P::HSLOT);
+        unsigned char *dst = stage0 + (size_t)s * P::HSLOT;
+        bulk_g2s(dst, src + (size_t)cta * P::HSLOT, P::HSLOT, &full[s]);     // the slot image is cut per CTA (slot_off)
+      }
+    }
+  } else if (warp == 1) {
+    if (cta != 0) {
+      // ===================== peer: relay "my half of slot s has landed" to the leader =====================
+      const long long mine = pair0 < pairs ? (pairs - pair0 + pstride - 1) / pstride : 0;
+      const long long total = mine * PER_TILE;
+      uint32_t slot = 0, slot_phase = 0;
+      for (long long it = 0; it < total; ++it) {
+        mbar_spin(&full[slot], slot_phase, err);
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&pfull[slot]), 0));
+        __syncwarp();
+        if (++slot == (uint32_t)P::SLOTS) { slot = 0; slot_phase ^= 1; }
+      }
+    } else {
+      // ===================== leader: MMA issuer for the pair =====================
+      const uint32_t idesc = idesc_bf16(256, C::DP);
+      constexpr uint32_t lbo_a = 128 * 16, lbo_b = P::HRUN;
+      constexpr uint64_t A_STEP = (2 * lbo_a) >> 4;
+      const uint64_t ah0 = smem_desc(smem_u32(A_hi), lbo_a, 128), al0 = smem_desc(smem_u32(A_lo), lbo_a, 128);
+      const uint64_t eh0 = smem_desc(smem_u32(E), lbo_a, 128);
+      const uint64_t bh0 = smem_desc(smem_u32(stage0), lbo_b, 128);
+      uint32_t slot = 0, slot_phase = 0, kphase = 0, ephase = 0, f0phase = 0, f1phase = 0;
+      auto wait_kstep = [&](int ks) {
+        mbar_wait(&kready[ks], kphase, err);
+        tc_fence_after();
+      };
+      auto wait_bar = [&](uint64_t *bar, uint32_t &phase) {
+        mbar_wait(bar, phase, err);
+        phase ^= 1;
+        tc_fence_after();
+      };
+      auto take_slot = [&](uint64_t &bh, uint64_t *&release) {
+#ifndef NSDP_PAIR_NOWAIT     // (experiment: garbage results, pure MMA issue / execution rate)
+        mbar_spin(&full[slot], slot_phase, err);
+        mbar_spin(&pfull[slot], slot_phase, err);
+#endif
+        tc_fence_after();
+        bh = bh0 + (uint64_t)slot * (P::HSLOT >> 4);
+        release = &empty[slot];
+        if (++slot == (uint32_t)P::SLOTS) { slot = 0; slot_phase ^= 1; }
+      };
+      auto gemm_a = [&](uint32_t d, bool follow) {
+        for (int ks = 0; ks < KS; ++ks) {
+          uint64_t bh, *rel;
+          if (follow) wait_kstep(ks);
+          take_slot(bh, rel);
+          if (elect_one()) {
+            const uint64_t ah = ah0 + ks * A_STEP, al = al0 + ks * A_STEP;
+            mma_bf16_pair(d, ah, bh, idesc, ks > 0);
+            mma_bf16_pair(d, al, bh, idesc, true);
+            mma_bf16_pair(d, ah, bh + (P::HSLAB >> 4), idesc, true);
+            mma_commit_pair(rel);
+          }
+        }
+      };
+      auto gemm_e = [&](uint32_t d) {
+        for (int ks = 0; ks < ES; ++ks) {
+          uint64_t bh, *rel;
+          take_slot(bh, rel);
+          if (elect_one()) {
+            const uint64_t eh = eh0 + ks * A_STEP;
+            mma_bf16_pair(d, eh, bh, idesc, true);
+            mma_bf16_pair(d, eh, bh + (P::HSLAB >> 4), idesc, true);
+            mma_commit_pair(rel);
+          }
+        }
+      };
+      for (long long pr = pair0; pr < pairs; pr += pstride) {
+        TR(100);
+        wait_bar(free1, f1phase);
+        TR(101);
+        gemm_a(tmem_base + C::ACC1_COL, true);          // GEMM1b: acc1 = H Wd2^T + E T2
+        kphase ^= 1;
+        wait_bar(e_ready, ephase);
+        gemm_e(tmem_base + C::ACC1_COL);
+        TR(102);
+        wait_bar(free0, f0phase);
+        TR(103);
+        gemm_a(tmem_base, false);                       // GEMM1a: acc0 = H W'^T + E T1
+        gemm_e(tmem_base);
+        if (elect_one()) mma_commit_pair(acc_done);
+        TR(110);
+        wait_bar(free0, f0phase);
+        TR(111);
+        gemm_a(tmem_base, true);                        // GEMM2: acc0 = G Wg2^T
+        if (elect_one()) mma_commit_pair(acc_done);
+        TR(113);
+        kphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== workers (both CTAs): one TMEM lane = one pair row of this CTA's tile =====================
+    const int ww = warp - 2;
+    const int quarter = warp & 3;
+    const int part = ww >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t done_phase = 0;
+    constexpr int NQ = (C::CHUNKS + C::NPART - 1) / C::NPART;
+    constexpr int NE = (C::E_COLS / 8 + C::NPART - 1) / C::NPART;
+    const int g8 = lane & 7;
+    constexpr size_t TB = saved_tile_bytes<C>();
+    const size_t sv_st = (size_t)(r >> 4) * (size_t)(2 * C::DP * 32) + (size_t)(r & 15) * 16;
+    const size_t sv_f32 = (size_t)r * 32;
+    // the leader's barriers, cluster-space addresses (valid from both CTAs)
+    const uint32_t kready0 = mapa_u32(smem_u32(kready), 0), e_ready_l = mapa_u32(smem_u32(e_ready), 0);
+    const uint32_t free0_l = mapa_u32(smem_u32(free0), 0), free1_l = mapa_u32(smem_u32(free1), 0);
+
+    auto chunk_done = [&](int ch) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(kready0 + (uint32_t)(ch >> 1) * 8u);
+    };
+    auto release = [&](uint32_t bar_l) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_l);
+    };
+    // tile of this CTA inside pair pr: shape b = pr / tpp, tile 2 (pr % tpp) + cta of the shape (may not exist: all rows off)
+    auto tile_of = [&](long long pr, long long &tile) -> bool {
+      const long long b = pr / tpp;
+      const int tin = 2 * (int)(pr - b * tpp) + (int)cta;
+      tile = b * tpb + tin;
+      return pr < pairs && tin < tpb;
+    };
+    auto row_info = [&](long long pr) {
+      long long tile;
+      RowInfoPB ri;
+      if (tile_of(pr, tile)) {
+        ri = row_info_pb<C>(a, tile, r, krows, tpb);
+      } else {
+        ri.c = -1; ri.j = -1; ri.rx = ri.ry = ri.rz = 0.f; ri.flag = 0.f;
+      }
+      return ri;
+    };
+    auto gen_operands = [&](const RowInfoPB &ri, long long pr) {
+      long long tile;
+      const bool sv = tile_of(pr, tile) && saved;
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::E_COLS / 8) {
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if ((ri.j >> 3) == ch) {
+            const uint32_t one = (ri.j & 1) ? 0x3F800000u : 0x00003F80u;
+            const int w = (ri.j & 7) >> 1;
+            e.x = w == 0 ? one : 0u; e.y = w == 1 ? one : 0u; e.z = w == 2 ? one : 0u; e.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(E + canon_off(128, r, ch * 8)) = e;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(e_ready_l);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          const int k0 = ch * 8;
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w0 = wd0s[k0 + j];
+            const float pre = fmaf(w0.x, ri.rx, fmaf(w0.y, ri.ry, fmaf(w0.z, ri.rz, w0.w)));
+            h[j] = ri.flag * fmaxf(pre, 0.f);
+          }
+          uint4 hi, lo;
+          split2(h[0], h[1], hi.x, lo.x);
+          split2(h[2], h[3], hi.y, lo.y);
+          split2(h[4], h[5], hi.z, lo.z);
+          split2(h[6], h[7], hi.w, lo.w);
+          const uint32_t off = canon_off(128, r, k0);
+          *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+          *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+          if (sv) {
+            unsigned char *p = saved + (size_t)tile * TB + sv_st + (size_t)ch * 256;
+            *reinterpret_cast<uint4 *>(p) = hi;
+            *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+          }
+          chunk_done(ch);
+        }
+      }
+    };
+
+    release(free0_l);
+    release(free1_l);
+    RowInfoPB ri = row_info(pair0);
+    if (pair0 < pairs) gen_operands(ri, pair0);
+    for (long long pr = pair0; pr < pairs; pr += pstride) {
+      long long tile;
+      const bool sv = tile_of(pr, tile) && saved;
+      const bool row_on = ri.c >= 0;
+      if (tid == 64) TR(200);
+      // ---- epilogue 1: G = relu(acc0 + pc) -> A operand (acc0 to registers first: GEMM2 overwrites it) ----------------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+      if (tid == 64) TR(202);
+      {
+        uint32_t gp[NQ][8];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) tmem_ld8_nowait(trow + ch * 8, gp[q]);
+        }
+        tmem_ld_wait();
+        release(free0_l);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int ch = part + q * C::NPART;
+          if (ch < C::CHUNKS) {
+            const int k0 = ch * 8;
+            float g[8];
+            pin8(gp[q]);
+            const float4 p0 = *reinterpret_cast<const float4 *>(pcs + k0), p1 = *reinterpret_cast<const float4 *>(pcs + k0 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaxf(__uint_as_float(gp[q][j]) + pv[j], 0.f);
+            uint4 hi, lo;
+            split2(g[0], g[1], hi.x, lo.x);
+            split2(g[2], g[3], hi.y, lo.y);
+            split2(g[4], g[5], hi.z, lo.z);
+            split2(g[6], g[7], hi.w, lo.w);
+            const uint32_t off = canon_off(128, r, k0);
+            *reinterpret_cast<uint4 *>(A_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(A_lo + off) = lo;
+            if (sv) {
+              unsigned char *p = saved + (size_t)(tiles + tile) * TB + sv_st + (size_t)ch * 256;
+              *reinterpret_cast<uint4 *>(p) = hi;
+              *reinterpret_cast<uint4 *>(p + C::DP * 32) = lo;
+            }
+            chunk_done(ch);
+          }
+        }
+      }
+      if (tid == 64) TR(204);
+      // ---- while GEMM2 runs: the next pair's row description ----------------------------------------------------------
+      const long long ci_grp = __shfl_sync(0xffffffffu, ri.c, lane & ~7);
+      const bool has_next = pr + pstride < pairs;
+      const RowInfoPB nxt = row_info(pr + pstride);
+
+      // ---- GEMM2 done: s = acc1 -> registers, then the next tile's operands (GEMM1b of the next pair trails them) ------
+      mbar_wait(acc_done, done_phase, err);
+      done_phase ^= 1;
+      tc_fence_after();
+      if (tid == 64) TR(206);
+      uint32_t sreg[NQ][8];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) tmem_ld8_nowait(trow + C::ACC1_COL + ch * 8, sreg[q]);
+      }
+      tmem_ld_wait();
+      release(free1_l);
+      if (has_next) gen_operands(nxt, pr + pstride);
+      if (tid == 64) TR(208);
+
+      // ---- epilogue 2: softmax over the 8 rows of a centre; out = sum w * (acc1 + vc) ---------------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = part + q * C::NPART;
+        if (ch < C::CHUNKS) {
+          const int k0 = ch * 8;
+          float av[8], sv8[8];
+          tmem_ld8(trow + k0, av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv8[j] = __uint_as_float(sreg[q][j]);
+          if (sv) {
+            float4 *pa = reinterpret_cast<float4 *>(saved + (size_t)(2 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
+            float4 *ps = reinterpret_cast<float4 *>(saved + (size_t)(3 * tiles + tile) * TB + sv_f32 + (size_t)ch * 4096);
+            pa[0] = make_float4(av[0], av[1], av[2], av[3]); pa[1] = make_float4(av[4], av[5], av[6], av[7]);
+            ps[0] = make_float4(sv8[0], sv8[1], sv8[2], sv8[3]); ps[1] = make_float4(sv8[4], sv8[5], sv8[6], sv8[7]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] = row_on ? av[j] : -INFINITY;
+          group8_transpose(av, lane);
+          group8_transpose(sv8, lane);
+          const int col = k0 + g8;
+          const float vcc = vcs[col];
+          float mx = av[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) mx = fmaxf(mx, av[i]);
+          float se = 0.f, ses = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = __expf(av[i] - mx);
+            se += e;
+            ses = fmaf(e, sv8[i] + vcc, ses);
+          }
+          if (ci_grp >= 0 && col < D) {
+            const float inv = 1.f / se;
+            out[ci_grp * D + col] = ses * inv;
+            if (stats) {
+              stats[ci_grp * D + col] = mx;
+              stats[((long long)a.B * a.M + ci_grp) * D + col] = inv;
+            }
+          }
+        }
+      }
+      if (tid == 64) TR(207);
+      release(free0_l);
+      ri = nxt;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();            // nobody leaves while the peer may still touch this CTA's barriers / shared memory
+  if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+}
+
+// NSDP_FWD_PAIR=1 selects the CTA-pair kernel. It is bit-compatible with the single-CTA kernel (tests/test_gpu_vattn.py runs the
+// decoder cases through both) but NOT the default: measured on B200 (8 x 50 000 queries) the pair kernel needs 33.0 k cycles
+// per tile pair against 29.5 k per tile of the single-CTA kernel on each of the two SMs, i.e. 3.15 ms against 2.75 ms. With the
+// k-step hand-over the tiles are bound by the workers' epilogues (softmax, operand generation: ~18 k of the 29.5 k cycles),
+// not by the weight stream the pair halves; and the pair's slot ring has a longer round trip (commit -> both producers ->
+// L2 -> relay to the leader: ~5.5 k cycles for 12 half slots, 460 cycles per k-step against the 357 the MMAs need), which
+// the shared memory left over (7 KB) cannot cover with more slots. Without slot waits (garbage results, timing only) the
+// pair tile takes 28.0 k cycles: the ceiling of the variant is ~5 %.
+static bool fwd_pair_on() {
+  static const bool v = [] { const char *e = getenv("NSDP_FWD_PAIR"); return e && atoi(e) != 0; }();
+  return v;
+}
+
 template <class C>
 static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *workspace, size_t ws_bytes, cudaStream_t st) {
   const size_t tb = (size_t)a.B * table_bytes_per_shape<C>();
@@ -821,10 +1259,11 @@ static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *w
   int *err = (int *)(tables + tb);
   cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
-  pack_weights_kernel<C><<<64, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed);
+  const int pair = (fwd_pair_on() && C::NPART == 4) ? 1 : 0;
+  pack_weights_kernel<C><<<64, 256, 0, st>>>(a.wpt, a.wd2t, a.wg2t, a.D, packed, pair);
   int rc = check_launch();
   if (rc != NSDP_OK) return rc;
-  pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables);
+  pack_tables_kernel<C><<<128, 256, 0, st>>>(a, tables, pair);
   rc = check_launch();
   if (rc != NSDP_OK) return rc;
   const int tpb = (a.M + C::CENTRES - 1) / C::CENTRES;
@@ -838,6 +1277,20 @@ static int launch_oh(const nsdp_vattn_args &a, float *out, float *stats, void *w
 #ifdef NSDP_TRACE
   if (const char *tp = getenv("NSDP_TRACE_FWD_PTR")) trace = (unsigned long long *)strtoull(tp, nullptr, 0);
 #endif
+  if (pair) {
+    auto kern2 = vattn_fwd_oh2_kernel<C>;
+    static bool ready = false;
+    if (!ready) {
+      e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<C>::SMEM);
+      if (e != cudaSuccess) return cuda_rc(e);
+      ready = true;
+    }
+    const long long pairs = (long long)a.B * ((tpb + 1) / 2);
+    const long long slots = num_sms() / 2;
+    const int grid2 = 2 * (int)(pairs < slots ? pairs : slots);
+    kern2<<<grid2, C::THREADS, PairCfg<C>::SMEM, st>>>(a, packed, tables, out, stats, saved, tpb, tiles, err, trace);
+    return check_launch();
+  }
   kern<<<grid, C::THREADS, C::SMEM, st>>>(a, packed, tables, out, stats, saved, tpb, tiles, err, trace);
   return check_launch();
 }

@@ -229,8 +229,19 @@ constexpr size_t table_bytes_per_shape() {
   return (size_t)C::E_KSTEPS * 2 * C::SLOT_BYTES;   // per k-step: [T1 hi][T1 lo][T2 hi][T2 lo]
 }
 
+// Byte offset of element (row n, k inside the k-step) of the hi (lo = 0) or lo (lo = 1) slab inside a two-slab slot.
+// pair = 0: [hi slab][lo slab], each canonical over all DP rows. pair = 1 (CTA-pair kernels): the slot is cut by rows into
+// the two halves the two CTAs fetch, [CTA 0: hi half slab, lo half slab][CTA 1: ...], each half canonical over DP / 2 rows.
 template <class C>
-__global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__restrict__ out) {
+__device__ __forceinline__ uint32_t slot_off(int n, int kin, int lo, int pair) {
+  if (!pair) return (uint32_t)(lo * C::SLAB) + canon_off(C::DP, n, kin);
+  constexpr int NH = C::DP / 2;
+  const int c = n / NH, nn = n - c * NH;
+  return (uint32_t)(c * (NH * 64) + lo * (NH * 32) + (kin >> 3) * (NH * 16) + nn * 16 + (kin & 7) * 2);
+}
+
+template <class C>
+__global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__restrict__ out, int pair = 0) {
   // one thread per (shape b, table m, column n, anchor pair k)
   const int per = C::DP * (C::E_COLS / 2);
   const long long total = (long long)a.B * 2 * per;
@@ -257,9 +268,8 @@ __global__ void pack_tables_kernel(const nsdp_vattn_args a, unsigned char *__res
     split2(x[0], x[1], hi, lo);
     const int ks = k >> 4;
     unsigned char *base = out + (size_t)b * table_bytes_per_shape<C>() + (size_t)(ks * 2 + m) * C::SLOT_BYTES;
-    const uint32_t in_slab = canon_off(C::DP, n, k & 15);
-    *reinterpret_cast<uint32_t *>(base + in_slab) = hi;
-    *reinterpret_cast<uint32_t *>(base + C::SLAB + in_slab) = lo;
+    *reinterpret_cast<uint32_t *>(base + slot_off<C>(n, k & 15, 0, pair)) = hi;
+    *reinterpret_cast<uint32_t *>(base + slot_off<C>(n, k & 15, 1, pair)) = lo;
   }
 }
 

@@ -249,6 +249,32 @@ def test_vattn_tc_decoder_forward(M, shape_query, monkeypatch):
         assert (got_tc - want).abs().max().item() < 3e-5 * scale
 
 
+def test_vattn_decoder_forward_cta_pair_kernel():
+    """The CTA-pair variant of the decoder forward kernel (tcgen05 cta_group::2, NSDP_FWD_PAIR=1; not the default, see
+    csrc/vattn_tc.cu) against the fp32 CUDA-core kernel, in a fresh process (the switch is read once per process).
+    M = 777 leaves the last pair of every shape with one missing tile, M = 40000 is many pairs per CTA pair."""
+    import os, subprocess, sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import test_gpu_vattn as t
+from nsdp_b200 import ops
+for M, sq in ((16, True), (777, True), (40000, True)):
+    case = t._rand_case(B=3, M=M, N=100, K=7, D=200, has_global=True, seed=M, shape_query=sq)
+    dev = {k: (v.to(t.DEV).contiguous() if torch.is_tensor(v) else v) for k, v in case.items()}
+    ops.VATTN_IMPL = 2
+    got = ops.vector_attention(sign=1.0, **dev).cpu().double()
+    ops.VATTN_IMPL = 1
+    ref = ops.vector_attention(sign=1.0, **dev).cpu().double()
+    err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1.0)
+    assert err < 3e-5, (M, err)
+print("pair ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NSDP_FWD_PAIR="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "pair ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-activations"])
 def test_vattn_oh_backward_multi_segment(save, monkeypatch, stage_fmt):
     """Decoder shape large enough for several staging segments whose boundaries fall inside shapes (3 x 2250 tiles vs
