@@ -99,7 +99,7 @@ def _rank_main(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_rank_nccl_sharded_decode_and_data_parallel_training(schemas):
+def test_two_rank_nccl_sharded_decode_and_data_parallel_training(schemas, monkeypatch):
     import torch.multiprocessing as mp
     from nsdp_b200.model import build_model, optimizer_factory
     world, port = 2, _free_port()
@@ -116,7 +116,7 @@ def test_two_rank_nccl_sharded_decode_and_data_parallel_training(schemas):
         assert shard_err < 1e-6 and seen == [501]             # each rank decoded its (padded) half of the 1001 queries
     # single process, whole batch of 4, ordinary BatchNorm == 2 ranks x 2 shapes with syncbn
     cfg = synth.make_config("forward")
-    os.environ["NSDP_B200_DP"] = "0"
+    monkeypatch.setenv("NSDP_B200_DP", "0")     # this process only, this test only (later tests launch data-parallel jobs)
     model, train_on_batch, _, _ = build_model(cfg, device=DEV)
     model.load_state_dict(synth.named_state_dict([(k, s) for k, s in schemas["forward"]], seed=0))
     model.train()

@@ -120,6 +120,8 @@ def test_unchanged_train_py_data_parallel_under_torchrun(tmp_path):
     cfg_path, cfg = make_dataset.write(str(tmp_path / "dp"))
     out = cfg["experiment"]["out_dir"]
     env = dict(os.environ)
+    for k in ("NSDP_B200_DP", "RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)                  # nothing inherited from tests that ran earlier in this process
     env["PYTHONPATH"] = os.pathsep.join([SHIMS, ROOT, env.get("PYTHONPATH", "")])
     env["WANDB_MODE"] = "disabled"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",

@@ -16,6 +16,7 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 600 python bench.py --workload c3 --steps 10 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c3.json 2>> gpurun_out/bench.err; echo "c3 rc=$?"; tail -c 400 gpurun_out/bench_c3.json | head -c 400; echo
 timeout 600 python bench.py --forward-only --steps 20 --warmup 5 > gpurun_out/bench_fwd.json 2>> gpurun_out/bench.err; echo "fwd rc=$?"
 timeout 600 python bench.py --impl reference --ref-device cuda --forward-only --steps 10 --warmup 3 > gpurun_out/bench_ref_gpu_fwd.json 2>> gpurun_out/bench.err; echo "ref gpu fwd rc=$?"
+timeout 400 python tools/microbench_c4.py > gpurun_out/microbench_c4.json 2> gpurun_out/microbench_c4.err; echo "c4 rc=$?"
 WARM=6 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_r2_one_step.csv python tools/one_step.py > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
