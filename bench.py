@@ -496,9 +496,10 @@ def run_ours(args):
                 "executed_mma_tflops": executed_tflops, "executed_frac": executed_tflops / peaks["bf16_tflops"],
                 "note": "achieved counts ALGORITHMIC flops (SURVEY 8d: 2 x 1.6884 MFLOP per query); the tensor pipe executes "
                         "~5.5x that (bf16x3 split precision 3x on the chain, forward recompute 1.5x, 200->208 padding, one-hot table "
-                        "products, single-term fp16 reduction), reported as executed_mma_tflops; the chain kernel is serial per "
-                        "tile (GEMM -> epilogue -> GEMM, 39 % tensor-pipe active under ncu), the reduction streams the staged "
-                        "tiles from HBM (profiles/ncu_r2_summary.md)",
+                        "products, single-term fp16 reduction), reported as executed_mma_tflops; the chain kernel hands operands to "
+                        "the tensor pipe per k-step, its tile is bound by the workers' CUDA-core epilogues and by shared-memory "
+                        "bandwidth (43 % tensor-pipe active under ncu), the reduction streams the staged tiles from HBM "
+                        "(profiles/ncu_r2_summary.md, DESIGN.md section 4)",
                 "share_of_step": bwd_ms / (ms_total / args.steps),
                 "top_kernel_by_time": top[0],
                 "fwd_kernel": {"launch_ms": fwd_ms, "achieved": flops["vattn_fwd"] / (fwd_ms * 1e-3) / 1e12,
