@@ -307,6 +307,18 @@ int nsdp_emlp_bwd_f32(const nsdp_emlp_args *args, const float *t1, const float *
  * NSDP_STAGE_FMT=fp16 | bf16x2. The encoder's attention blocks and nsdp_fused_mlp_bwd_f32 always use bf16 hi + lo. */
 int nsdp_set_stage_format(int fmt);
 
+/* One optimizer step of torch.optim.Adam (amsgrad = False, maximize = False, capturable layout: the step count is a
+ * float32 device scalar per parameter) over `ntensors` parameter tensors in two launches: replaces `optimizer.step()` of the
+ * reference's train_on_batch_* (model/deformation_networks.py:72, model/flow_arbitrary.py:45; optimizer built by
+ * model/__init__.py:21-40). p / g / m / v / step: HOST arrays of device pointers (parameter, gradient, exp_avg, exp_avg_sq,
+ * step), numel: host array of element counts. All tensors contiguous fp32. Update rule of torch's fused Adam:
+ *   step += 1; g' = g + weight_decay p; m += (g' - m)(1 - beta1); v = beta2 v + (1 - beta2) g'^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps);
+ * the hyper-parameters are doubles (as torch holds them): 1 - beta and beta^step are formed in double, the rest in fp32. */
+int nsdp_adam_step_f32(int ntensors, float *const *p, const float *const *g, float *const *m, float *const *v,
+                       float *const *step, const long long *numel, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, void *stream);
+
 /* Hardware self-test of the tcgen05 / TMEM conventions the tensor-core kernels rely on:
  * D (128,N) = A (128,K) * B (N,K)^T in bf16 (split == 0) or bf16x3 split precision (split != 0), single CTA.
  * N % 16 == 0, 16 <= N <= 256, K % 16 == 0. *err (device int) is set to 1 if an mbarrier wait timed out.

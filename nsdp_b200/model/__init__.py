@@ -33,11 +33,14 @@ def optimizer_factory(config, parameters):
         group["momentum"] = config.get("momentum", 0.9)
         return schedule, torch.optim.SGD([group])
     if name == "Adam":
-        # same update rule and state_dict layout as the reference's torch.optim.Adam; on the GPU the whole step is one
-        # fused kernel instead of ~30 multi-tensor launches; capturable (step count on the device) so that the whole training
-        # step can be replayed as a CUDA graph (nsdp_b200/graph.py)
+        # same update rule and state_dict layout as the reference's torch.optim.Adam; on the GPU the whole step is two
+        # launches of the library (nsdp_b200/optim.py, csrc/adam.cu); capturable (step count on the device) so that the
+        # whole training step can be replayed as a CUDA graph (nsdp_b200/graph.py)
         fused = len(parameters) > 0 and all(p.is_cuda for p in parameters)
-        return schedule, torch.optim.Adam([group], fused=fused, capturable=fused)
+        if fused:
+            from nsdp_b200.optim import Adam
+            return schedule, Adam([group])
+        return schedule, torch.optim.Adam([group])
     raise NotImplementedError()
 
 
