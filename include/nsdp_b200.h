@@ -307,6 +307,12 @@ int nsdp_emlp_bwd_f32(const nsdp_emlp_args *args, const float *t1, const float *
  * NSDP_STAGE_FMT=fp16 | bf16x2. The encoder's attention blocks and nsdp_fused_mlp_bwd_f32 always use bf16 hi + lo. */
 int nsdp_set_stage_format(int fmt);
 
+/* Weight / bias gradient of `nn.Linear` with a narrow input (K <= 8 channels) on many rows, the backward of the encoder's
+ * input layer `enc_sdf` (model/encoder/pointransformer.py:25, :97) and of the projections folded through it:
+ *   dW (N,K) += dy (R,N)^T x (R,K);   db (N) += column sums of dy (db may be NULL).
+ * All row-major contiguous fp32; dW / db are ACCUMULATED into (zero them first for a plain gradient). */
+int nsdp_linear_narrow_dw_f32(const float *x, const float *dy, long long R, int K, int N, float *dW, float *db, void *stream);
+
 /* One optimizer step of torch.optim.Adam (amsgrad = False, maximize = False, capturable layout: the step count is a
  * float32 device scalar per parameter) over `ntensors` parameter tensors in two launches: replaces `optimizer.step()` of the
  * reference's train_on_batch_* (model/deformation_networks.py:72, model/flow_arbitrary.py:45; optimizer built by

@@ -113,6 +113,7 @@ SIGNATURES = {
     "nsdp_emlp_bwd_workspace_bytes": (_SZ, [C.POINTER(EmlpArgs)]),
     "nsdp_emlp_bwd_f32": (_I, [C.POINTER(EmlpArgs), _P, _P, _P, _P, _P, C.POINTER(EmlpGrads), _P, _SZ, _P]),
     "nsdp_set_stage_format": (_I, [_I]),
+    "nsdp_linear_narrow_dw_f32": (_I, [_P, _P, C.c_longlong, _I, _I, _P, _P, _P]),
     "nsdp_adam_step_f32": (_I, [_I, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "nsdp_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "nsdp_selftest_umma2": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),

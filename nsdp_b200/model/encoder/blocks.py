@@ -53,7 +53,7 @@ def _fused_linear_through(x_in: torch.Tensor, lin: nn.Linear, weights):
     into one [rows, c_in] x [c_in, sum d_out] product — (W lin.weight) x + W lin.bias — 30x fewer FLOPs than projecting the
     120-wide features (exact in real arithmetic; autograd carries the gradients back through the fold)."""
     wcat = torch.cat(list(weights), dim=0)
-    outs = F.linear(x_in, wcat @ lin.weight, torch.mv(wcat, lin.bias)).split([w.shape[0] for w in weights], dim=-1)
+    outs = ops.linear(x_in, wcat @ lin.weight, torch.mv(wcat, lin.bias)).split([w.shape[0] for w in weights], dim=-1)
     return [o.contiguous() for o in outs]
 
 

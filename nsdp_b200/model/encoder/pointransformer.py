@@ -8,6 +8,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from nsdp_b200 import ops
 from nsdp_b200.model.encoder.blocks import ElementwiseMLP, TransformerBlock, TransitionDown, fold_sites
 
 
@@ -69,7 +70,7 @@ class PointTransformerEncoder(nn.Module):
         folds = self._fold_all()
         if self.has_features:
             raw = xyz[:, :, 3:]
-            feats = self.enc_sdf(raw)
+            feats = ops.linear(raw, self.enc_sdf.weight, self.enc_sdf.bias)     # nn.Linear(4 -> 120) on B * N rows
             xyz = xyz[:, :, :3].contiguous()
             feats = self.transformer_begin(xyz, feats, feats_from=(raw, self.enc_sdf), folded=folds["begin"])
         else:

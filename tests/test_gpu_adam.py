@@ -82,3 +82,25 @@ def test_adam_step_is_capturable():
     for a, b in zip(ours, ref):
         assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
     assert float(o1.state[ours[0]]["step"]) == 5.0
+
+
+@pytest.mark.parametrize("R,K,N,bias", [(32768, 4, 360, True), (5000, 3, 120, False), (4096, 8, 129, True), (70000, 1, 7, True)])
+def test_linear_narrow_backward(R, K, N, bias):
+    """ops.linear (narrow input, many rows): the weight / bias gradient kernel against torch autograd in float64."""
+    from nsdp_b200 import ops
+    g = torch.Generator().manual_seed(R + K)
+    x = torch.randn(R, K, generator=g).to(DEV).requires_grad_(True)
+    w = torch.randn(N, K, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(DEV).requires_grad_(True) if bias else None
+    d_y = torch.randn(R, N, generator=g).to(DEV)
+    y = ops.linear(x, w, b)
+    y.backward(d_y)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(d_y.double())
+    assert torch.allclose(y.double(), yd, rtol=1e-5, atol=1e-5)
+    rel = lambda a, t: float((a.double() - t).norm() / t.norm())
+    assert rel(w.grad, wd.grad) < 2e-6 and rel(x.grad, xd.grad) < 2e-6
+    if bias:
+        assert rel(b.grad, bd.grad) < 2e-6
