@@ -63,13 +63,16 @@ def fold_pair_mlps(fc_delta: nn.Sequential, fc_gamma: nn.Sequential):
     wd2, bd2 = fc_delta[2].weight, fc_delta[2].bias
     wg0, bg0 = fc_gamma[0].weight, fc_gamma[0].bias
     wg2 = fc_gamma[2].weight
+    wp = wg0 @ wd2
     return dict(
         wd0=wd0.contiguous(), bd0=bd0.contiguous(),
         wd2t=wd2.t().contiguous(),
-        wpt=(wg0 @ wd2).t().contiguous(),
+        wpt=wp.t().contiguous(),
         wg2t=wg2.t().contiguous(),
         pc=torch.mv(wg0, bd2) + bg0,
         vc=bd2.contiguous(),
+        # the same matrices un-transposed, for the backward's data-gradient products (no gradient flows through these)
+        wd2n=wd2.detach().contiguous(), wpn=wp.detach(), wg2n=wg2.detach().contiguous(),
     )
 
 
@@ -96,8 +99,10 @@ def fold_sites(sites):
         bg0 = torch.stack([sites[i][1][0].bias for i in members])
         wg2 = torch.stack([sites[i][1][2].weight for i in members])
         wd2t = wd2.transpose(1, 2).contiguous()
-        wpt = torch.bmm(wg0, wd2).transpose(1, 2).contiguous()
+        wp = torch.bmm(wg0, wd2)
+        wpt = wp.transpose(1, 2).contiguous()
         wg2t = wg2.transpose(1, 2).contiguous()
+        wd2n, wpn, wg2n = wd2.detach(), wp.detach(), wg2.detach()
         pc = torch.bmm(wg0, bd2.unsqueeze(-1)).squeeze(-1) + bg0
         # projection folds: every (site, projection) pair is one batch entry
         owner = [(s, p) for s, i in enumerate(members) for p in sites[i][2]]
@@ -109,7 +114,7 @@ def fold_sites(sites):
         for s, i in enumerate(members):
             fd = sites[i][0]
             out[i] = (dict(wd0=fd[0].weight.contiguous(), bd0=fd[0].bias.contiguous(), wd2t=wd2t[s], wpt=wpt[s], wg2t=wg2t[s],
-                           pc=pc[s], vc=bd2[s]), per_site[s])
+                           pc=pc[s], vc=bd2[s], wd2n=wd2n[s], wpn=wpn[s], wg2n=wg2n[s]), per_site[s])
     return out
 
 

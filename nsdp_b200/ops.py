@@ -274,7 +274,8 @@ class _VectorAttention(torch.autograd.Function):
     inputs + the (B,M,D) result and softmax statistics — no [pairs, D] activation is saved."""
 
     @staticmethod
-    def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, grad_enabled=True):
+    def forward(ctx, xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign, grad_enabled=True,
+                wd2n=None, wpn=None, wg2n=None):
         tensors = dict(xyz_c=xyz_c, xyz_n=xyz_n, qp=qp, kp=kp, vp=vp, gq=gq, gv=gv, wd0=wd0, bd0=bd0, wd2t=wd2t,
                        wpt=wpt, wg2t=wg2t, pc=pc, vc=vc)
         for n, t in tensors.items():
@@ -305,15 +306,20 @@ class _VectorAttention(torch.autograd.Function):
         _count()
         ctx.sign = sign
         if need_bwd:
-            ctx.save_for_backward(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats, saved)
+            ctx.save_for_backward(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats, saved,
+                                  wd2n, wpn, wg2n)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats, saved = ctx.saved_tensors
+        (xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, out, stats, saved,
+         wd2n, wpn, wg2n) = ctx.saved_tensors
         d_out = d_out.contiguous()
-        # the data-gradient GEMMs need the un-transposed matrices as K-major operands
-        wd2, wp, wg2 = wd2t.t().contiguous(), wpt.t().contiguous(), wg2t.t().contiguous()
+        # the data-gradient GEMMs need the un-transposed matrices as K-major operands: the caller's own (it transposed them
+        # to make wd2t / wpt / wg2t) or three small transposes here
+        wd2 = wd2n if wd2n is not None else wd2t.t().contiguous()
+        wp = wpn if wpn is not None else wpt.t().contiguous()
+        wg2 = wg2n if wg2n is not None else wg2t.t().contiguous()
         a = _vattn_args(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, ctx.sign, wd2, wp, wg2)
         if saved is not None and a.impl != 1:
             a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
@@ -353,13 +359,22 @@ class _VectorAttention(torch.autograd.Function):
         _count()
         return (g["d_xyz_c"], g["d_xyz_n"], None, g["d_qp"], g["d_kp"], g["d_vp"], g["d_gq"], g["d_gv"], g["d_wd0"],
                 g["d_bd0"], g["d_wd2t"] if need[10] else None, g["d_wpt"] if need[11] else None,
-                g["d_wg2t"] if need[12] else None, g["d_pc"], g["d_vc"], None, None)
+                g["d_wg2t"] if need[12] else None, g["d_pc"], g["d_vc"], None, None, None, None, None)
 
 
-def vector_attention(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign=1.0, gq=None, gv=None):
-    """Fused pair-level vector attention (see nsdp_vattn_args in include/nsdp_b200.h)."""
+def vector_attention(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign=1.0, gq=None, gv=None,
+                     wd2n=None, wpn=None, wg2n=None):
+    """Fused pair-level vector attention (see nsdp_vattn_args in include/nsdp_b200.h). `wd2n` / `wpn` / `wg2n`: optional
+    contiguous, DETACHED copies of the three d x d matrices in their natural (un-transposed) layout, i.e. wd2t.t() etc.; a
+    caller that built the transposed operands from them passes them along and saves the backward three transposes."""
+    def nat(n, t):
+        if n is None:
+            return None
+        if n.requires_grad or not n.is_contiguous() or n.shape != t.shape:
+            raise ValueError("wd2n / wpn / wg2n: detached, contiguous, same shape as the transposed operand")
+        return n
     return _VectorAttention.apply(xyz_c, xyz_n, idx, qp, kp, vp, gq, gv, wd0, bd0, wd2t, wpt, wg2t, pc, vc, float(sign),
-                                  torch.is_grad_enabled())
+                                  torch.is_grad_enabled(), nat(wd2n, wd2t), nat(wpn, wpt), nat(wg2n, wg2t))
 
 
 def _tail_args(lat2d, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo) -> TailArgs:

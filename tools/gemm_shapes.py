@@ -26,3 +26,10 @@ for e in rows[:24]:
         tot += e.device_time_total
         print(f"{e.device_time_total / 1e3:8.3f} ms  x{e.count:3d}  {e.key:12s} {e.input_shapes}")
 print("sum of listed mm/addmm/bmm:", round(tot / 1e3, 3), "ms")
+print("---- other ATen ops by device time (self)")
+others = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.key not in ("aten::mm", "aten::addmm", "aten::bmm") and e.self_device_time_total > 0]
+others.sort(key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in others)
+print("total", round(tot / 1e3, 3), "ms over", sum(e.count for e in others), "calls")
+for e in others[:28]:
+    print(f"{e.self_device_time_total / 1e3:8.3f} ms  x{e.count:3d}  {e.key:28s} {str(e.input_shapes)[:110]}")
