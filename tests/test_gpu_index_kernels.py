@@ -175,3 +175,42 @@ def test_gather_and_group():
     if ref is not None:
         assert torch.equal(ref.gather_points(feats.to(DEV), idx1.to(DEV)), g1)
         assert torch.equal(ref.group_points(feats.to(DEV), idx2.to(DEV)), g2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vectors minted by the LIVE reference's own torch code (tests/golden/make_golden_index.py; inputs stored in the fixture)
+# ---------------------------------------------------------------------------------------------------------------------
+def _index_gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "index_reference.npz"))
+
+
+def test_fps_equals_reference_torch_fps_vectors():
+    """model/utils.py:73-93 `farthest_point_sample` with start index 0 — and, where oracle/_ref exists, the reference's CUDA
+    kernel on the same stored clouds."""
+    gold = _index_gold()
+    names = sorted({k.split("::")[1] for k in gold.keys() if k.startswith("fps::")})
+    assert len(names) == 6
+    ref = ref_ext.load()
+    for name in names:
+        xyz = torch.from_numpy(gold[f"fps::{name}::xyz"]).to(DEV).contiguous()
+        want = torch.from_numpy(gold[f"fps::{name}::idx"])
+        got = ops.furthest_point_sampling(xyz, want.shape[1]).cpu()
+        assert torch.equal(got, want), f"{name}: first mismatch at {(got != want).nonzero()[:3].tolist()}"
+        if ref is not None:
+            assert torch.equal(ref.furthest_point_sampling(xyz, want.shape[1]).cpu(), want), name
+
+
+def test_knn_equals_reference_argsort_vectors():
+    """square_distance(q, r).argsort()[:, :, :k] of the live reference (model/utils.py:39-55, encoder/blocks.py:101-102) on
+    rows without distance ties: indices and distances bit-exact."""
+    gold = _index_gold()
+    names = sorted({k.split("::")[1] for k in gold.keys() if k.startswith("knn::")})
+    assert len(names) == 4
+    for name in names:
+        q = torch.from_numpy(gold[f"knn::{name}::query"]).to(DEV).contiguous()
+        r = torch.from_numpy(gold[f"knn::{name}::ref"]).to(DEV).contiguous()
+        want = torch.from_numpy(gold[f"knn::{name}::idx"])
+        got, d2 = ops.knn(q, r, want.shape[2], return_d2=True)
+        assert torch.equal(got.cpu(), want), name
+        assert torch.equal(d2.cpu(), torch.from_numpy(gold[f"knn::{name}::d2"])), name
