@@ -180,8 +180,8 @@ def graphed_forward(model, inputs, eager_fn):
     """eager_fn(*inputs) -> tensor, for a model in eval mode with gradients disabled: no side effects, so after WARMUP eager
     calls per input-shape signature the forward is captured and replayed (the result is copied out of the graph's static
     output buffer). Everything else runs eager_fn directly."""
-    if (not ENABLED or ops.TIMING or model.training or torch.is_grad_enabled() or torch.cuda.is_current_stream_capturing()
-            or not all(torch.is_tensor(t) and t.is_cuda for t in inputs)):
+    if (not ENABLED or ops.TIMING or model.training or torch.is_grad_enabled()
+            or not all(torch.is_tensor(t) and t.is_cuda for t in inputs) or torch.cuda.is_current_stream_capturing()):
         return eager_fn(*inputs)
     per_model = _FWD_STATE.setdefault(model, {})
     sig = tuple((tuple(t.shape), t.dtype, str(t.device)) for t in inputs)
