@@ -296,3 +296,38 @@ def test_forward_net_inference_encodes_once_with_the_references_result(contracts
     assert abs(loss - float(orc.l2_loss(want_verts, verts_tgt))) < 1e-12
     loss0, _ = infer(model, data, None, compute_loss=False)
     assert loss0 == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ablation blocks: `encoder: pointnet++`, `decoder: interp`
+# ---------------------------------------------------------------------------------------------------------------------
+def test_ablation_model_on_contracts(contracts):
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(gdir, "ablation_reference.npz"))
+    with open(os.path.join(gdir, "ablation_schema.json")) as f:
+        schema = json.load(f)
+    model, *_ = build_model(synth.make_ablation_config(), device="cpu")
+    model.load_state_dict(synth.named_state_dict([(k, s) for k, s in schema], seed=0))
+    model.eval()
+    batch = synth.forward_batch(1, 1024, 2048, seed=1234, fp16_grid=False)
+    with torch.no_grad():
+        enc = model.encode(batch["surface_samples_inputs"])
+        out = model.decode(batch["space_samples_src"], enc)
+    np.testing.assert_array_equal(enc["anchors"].numpy(), gold["c1_anchors"])
+    np.testing.assert_allclose(enc["z"].numpy(), gold["c1_z"], atol=5e-5, rtol=1e-4)
+    assert _mean_l2(out.numpy(), gold["c1_flow"]) < 2e-6
+    model.train()
+    b = synth.forward_batch(2, 768, 640, seed=5, fp16_grid=False)
+    q = b["space_samples_src"].clone().requires_grad_(True)
+    pred = model.decode(q, model.encode(b["surface_samples_inputs"]))
+    loss = orc.l2_loss(pred, b["space_samples_tgt"])
+    loss.backward()
+    assert abs(loss.item() - float(gold["train_loss"])) < 1e-6
+    assert _mean_l2(pred.detach().numpy(), gold["train_pred"]) < 2e-5      # fp32 through train-mode BatchNorm; GPU bar 1e-4
+    # d/d query of an fp32 run vs another fp32 run: ReLU-kink flips dominate (no kink mask in this fixture)
+    assert np.linalg.norm(q.grad.numpy() - gold["train_dq"]) / np.linalg.norm(gold["train_dq"]) < 1e-2
+    norms = np.array([float(p.grad.norm()) if p.grad is not None else -1.0 for _, p in model.named_parameters()])
+    has = gold["train_gradnorms"] > 1e-6
+    assert np.all(norms[has] > 0) and np.median(np.abs(norms[has] / gold["train_gradnorms"][has] - 1)) < 1e-3
