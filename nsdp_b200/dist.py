@@ -292,7 +292,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
         C = x.shape[1]
-        packed = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+        packed = torch.empty(2 * C + 1, dtype=x.dtype if x.dtype == torch.float64 else torch.float32, device=x.device)
         packed[:C] = x.sum(0)
         packed[C:2 * C] = (x * x).sum(0)
         packed[2 * C] = x.shape[0]

@@ -211,3 +211,81 @@ def test_inactive_without_process_group():
         nd.shard_batch({"x": torch.zeros(5, 1)}, rank=0, world=2)
     pts = torch.rand(1, 5, 3)
     assert torch.equal(nd.sharded_decode(lambda p: p + 1.0, pts), pts + 1.0)   # no process group: plain decode
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the REAL TDNet mirror through the real entry points (build_model joins the job, optimizer_factory, train_on_batch), with the
+# header's kernel contracts standing in for the CUDA kernels (tests/helpers/contracts.py): SURVEY.md section 4 "distributed"
+# ---------------------------------------------------------------------------------------------------------------------
+def _tdnet_batch():
+    from nsdp_b200 import synth
+    b = synth.forward_batch(2, 384, 160, seed=41, fp16_grid=False)
+    return {k: b[k].double() for k in ("surface_samples_inputs", "space_samples_src", "space_samples_tgt")}
+
+
+def _tdnet_train(world_rank=None):
+    """Two Adam steps of the forward TDNet in float64 on this process's share of the 2-shape batch; returns losses + state."""
+    from helpers import contracts
+    from nsdp_b200 import synth
+    from nsdp_b200.model import build_model, optimizer_factory
+    contracts.install()
+    cfg = synth.make_config("forward")
+    torch.manual_seed(7 if not world_rank else 1000 + world_rank)       # ranks > 0 start from OTHER weights: rank 0's must win
+    model, train_on_batch, *_ = build_model(cfg, device="cpu")
+    if not world_rank:
+        schema = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+        model.load_state_dict(synth.named_state_dict(schema, seed=0))
+        if world_rank == 0:
+            nd.broadcast_parameters(model)                               # what train.py's checkpoint loading + first step amount to
+    else:
+        nd.broadcast_parameters(model)
+    model.double()
+    model.train()
+    _, opt = optimizer_factory(cfg["training"], model.parameters())
+    assert type(opt) is torch.optim.Adam                                # the library's fused Adam is for CUDA parameters only
+    data = _tdnet_batch()
+    if world_rank is not None:
+        data = nd.shard_batch(data)
+    losses = [train_on_batch(model, opt, data, cfg) for _ in range(2)]
+    return losses, {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def _tdnet_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      NSDP_B200_SYNCBN="1", NSDP_B200_BUCKET_BYTES=str(1 << 20))
+    torch.set_num_threads(2)
+    losses, sd = _tdnet_train(rank)                                     # build_model creates the gloo group from the environment
+    assert nd.is_active()
+    q.put((rank, losses, sd))
+    td.destroy_process_group()
+
+
+def test_tdnet_two_ranks_with_syncbn_equal_one_process_on_the_whole_batch():
+    """2 ranks x 1 shape (BatchNorm statistics over both ranks, averaged gradients, bucketed all-reduce from autograd hooks)
+    == 1 process x 2 shapes, after two Adam steps of the real model: identical weights and BatchNorm buffers (float64: 1e-9),
+    and the mean of the per-rank losses is the single-process loss."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tdnet_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref_losses, ref_sd = _tdnet_train(None)
+    for step in range(2):
+        assert abs(0.5 * (res[0][1][step] + res[1][1][step]) - ref_losses[step]) < 1e-9
+    assert ref_losses[1] != ref_losses[0]                               # the optimizer moved the weights
+    for rank, _, sd in res:
+        assert list(sd.keys()) == list(ref_sd.keys())
+        for k, v in ref_sd.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v) == 2, k
+            else:
+                np.testing.assert_allclose(sd[k], v, atol=1e-9, rtol=1e-7, err_msg=f"rank {rank}: {k}")
+    for k in ref_sd:                                                    # and the replicas agree with each other bit for bit
+        assert np.array_equal(res[0][2][k], res[1][2][k]), k

@@ -9,80 +9,21 @@ the unmodified mirror modules then run on CPU tensors against (a) the vectors th
 (tests/golden/tdnet_reference.npz, make_golden.py) and (b) the oracle in float64 (1e-9: pure algebra, no rounding slack).
 kernel == contract (GPU tests) and contract + host code == reference (here) give kernel path == reference at block level.
 
-Test infrastructure: the stand-ins live here, never in the package — the product has no CPU path (tests/test_abi.py)."""
+Test infrastructure: the stand-ins live in tests/helpers/contracts.py, never in the package — the product has no CPU path (tests/test_abi.py)."""
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
-from nsdp_b200 import ops, synth
+from nsdp_b200 import synth
 from nsdp_b200.model import build_model
 from oracle import tdnet_oracle as orc
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# the contracts of include/nsdp_b200.h, restated (any dtype, differentiable)
-# ---------------------------------------------------------------------------------------------------------------------
-def contract_vector_attention(xyz_c, xyz_n, idx, qp, kp, vp, wd0, bd0, wd2t, wpt, wg2t, pc, vc, sign=1.0, gq=None, gv=None,
-                              wd2n=None, wpn=None, wg2n=None):
-    """nsdp_vattn_args (include/nsdp_b200.h, "Vector attention core over neighbourhoods")."""
-    B, M, _ = xyz_c.shape
-    N = xyz_n.shape[1]
-    for nat, t in ((wd2n, wd2t), (wpn, wpt), (wg2n, wg2t)):        # the un-transposed copies must BE the transposes
-        if nat is not None:
-            assert not nat.requires_grad and torch.equal(nat, t.detach().t())
-    if idx is None:
-        idx = torch.arange(N).view(1, 1, N).expand(B, M, N)
-    idx = idx.long()
-    K = idx.shape[2]
-    gather = lambda t: torch.gather(t, 1, idx.reshape(B, M * K, 1).expand(-1, -1, t.shape[-1])).reshape(B, M, K, -1)
-    rel = sign * (xyz_c[:, :, None] - gather(xyz_n))
-    h = F.relu(rel @ wd0.t() + bd0)
-    dlt = h @ wd2t
-    pre = h @ wpt + pc
-    if qp is not None:
-        pre = pre + qp[:, :, None]
-    if kp is not None:
-        pre = pre - gather(kp)
-    a = F.relu(pre) @ wg2t
-    val = vc + dlt
-    if vp is not None:
-        val = val + gather(vp)
-    if gq is not None:
-        a = torch.cat([a, (F.relu(gq) @ wg2t)[:, None, None, :].expand(-1, M, -1, -1)], dim=2)
-        val = torch.cat([val, gv[:, None, None, :].expand(-1, M, -1, -1)], dim=2)
-    return (torch.softmax(a, dim=2) * val).sum(dim=2)
-
-
-def contract_resnet_tail(lat, wc_t, bc, w0_t, b0, w1_t, b1, wo_t, bo):
-    """nsdp_tail_args: net = init(lat); for i: net += fc_c[i](lat); net += fc_1[i](relu(fc_0[i](relu(net)))); out = fc_out(relu(net))."""
-    H = w0_t.shape[-1]
-    pre = lat @ wc_t + bc
-    net = pre[:, :H]
-    for i in range(w0_t.shape[0]):
-        net = net + pre[:, (1 + i) * H:(2 + i) * H]
-        net = net + F.relu(F.relu(net) @ w0_t[i] + b0[i]) @ w1_t[i] + b1[i]
-    return F.relu(net) @ wo_t + bo
-
-
-def contract_elementwise_mlp(x, conv1, bn1, conv2, bn2, bn3):
-    """nsdp_emlp_args: bn3(x + relu(bn2(conv2(relu(bn1(conv1 x)))))) over the rows of x, torch BatchNorm1d semantics."""
-    B, n, C = x.shape
-    rows = x.reshape(B * n, C)
-    t1 = F.linear(rows, conv1.weight.squeeze(-1), conv1.bias)
-    t2 = F.linear(F.relu(bn1(t1)), conv2.weight.squeeze(-1), conv2.bias)
-    return bn3(rows + F.relu(bn2(t2))).reshape(B, n, C)
-
-
 @pytest.fixture
 def contracts(monkeypatch):
-    """Index kernels -> the C oracle (bit-exact contract, pinned in tests/test_index_golden.py); fused kernels -> the header."""
-    monkeypatch.setattr(ops, "vector_attention", contract_vector_attention)
-    monkeypatch.setattr(ops, "resnet_tail", contract_resnet_tail)
-    monkeypatch.setattr(ops, "elementwise_mlp", contract_elementwise_mlp)
-    monkeypatch.setattr(ops, "linear", F.linear)
-    monkeypatch.setattr(ops, "knn", lambda q, r, k, return_d2=False: orc.knn(q, r, k, return_d2=return_d2))
-    monkeypatch.setattr(ops, "furthest_point_sampling", lambda xyz, m: orc.fps(xyz, m))
+    """The header's kernel contracts (tests/helpers/contracts.py) stand in for the ops entry points, for this test only."""
+    from helpers import contracts as hc
+    hc.install(monkeypatch.setattr)
 
 
 def _model(schemas, mtype, cfg=None, dtype=torch.float32):
