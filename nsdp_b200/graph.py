@@ -37,11 +37,17 @@ _STATE = weakref.WeakKeyDictionary()      # model -> {signature: _Entry}
 
 
 class _Entry:
-    __slots__ = ("calls", "graph", "static", "loss", "lrs", "launches", "failed", "opt_graph")
+    __slots__ = ("calls", "graph", "static", "loss", "lrs", "launches", "failed", "opt_graph", "opt_ref")
 
-    def __init__(self):
+    def __init__(self, optimizer=None):
         self.calls, self.graph, self.static, self.loss = 0, None, None, None
         self.lrs, self.launches, self.failed, self.opt_graph = None, 0, False, None
+        # the signature holds id(optimizer), and an id can be reused by a NEW optimizer once the old one is collected: the
+        # captured launches would then keep updating the dead optimizer's state tensors
+        self.opt_ref = weakref.ref(optimizer) if optimizer is not None else None
+
+    def stale(self, optimizer) -> bool:
+        return self.opt_ref is not None and self.opt_ref() is not optimizer
 
 
 def _signature(model, optimizer, data_dict, keys):
@@ -95,8 +101,8 @@ def graphed_train_step(model, optimizer, data_dict, forward_backward, finish, ke
     per_model = _STATE.setdefault(model, {})
     sig = _signature(model, optimizer, data_dict, keys)
     e = per_model.get(sig)
-    if e is None:
-        e = per_model[sig] = _Entry()
+    if e is None or e.stale(optimizer):
+        e = per_model[sig] = _Entry(optimizer)
     if e.failed:
         return eager_fn(model, optimizer, data_dict).item()
     lrs = _lrs(optimizer)
