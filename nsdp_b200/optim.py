@@ -43,6 +43,7 @@ class Adam(torch.optim.Adam):
             return super().step(closure)
         from nsdp_b200 import ops
         stream = torch.cuda.current_stream().cuda_stream
+        plans = []        # every group is validated BEFORE the first launch: falling back to torch half-way would step twice
         for group in self.param_groups:
             ps, gs, ms, vs, ss, ns = [], [], [], [], [], []
             for p in group["params"]:
@@ -58,9 +59,10 @@ class Adam(torch.optim.Adam):
                     return super().step(closure)      # e.g. a state loaded from a non-capturable optimizer: torch converts it
                 ps.append(p.data_ptr()); gs.append(p.grad.data_ptr()); ms.append(m.data_ptr()); vs.append(v.data_ptr())
                 ss.append(s.data_ptr()); ns.append(p.numel())
+            if ps:
+                plans.append((group, ps, gs, ms, vs, ss, ns))
+        for group, ps, gs, ms, vs, ss, ns in plans:
             n = len(ps)
-            if n == 0:
-                continue
             arr = C.c_void_p * n
             beta1, beta2 = group["betas"]
             rc = _lib.lib().nsdp_adam_step_f32(n, arr(*ps), arr(*gs), arr(*ms), arr(*vs), arr(*ss), (C.c_longlong * n)(*ns),
