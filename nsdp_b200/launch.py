@@ -93,13 +93,24 @@ def rewrite_argv_for_rank(argv, rank: int, world: int, scratch_dir: str):
     return argv
 
 
+def device_for_local_rank(local_rank: int, visible) -> str:
+    """The CUDA_VISIBLE_DEVICES value that makes the script's hard-wired `cuda:0` this rank's GPU: the local_rank-th entry of
+    the devices the job was given (indices or UUIDs), or the plain index when the job sees every GPU."""
+    ids = [v.strip() for v in (visible or "").split(",") if v.strip()]
+    if not ids:
+        return str(local_rank)
+    if local_rank >= len(ids):
+        raise SystemExit(f"nsdp_b200.launch: LOCAL_RANK={local_rank} but CUDA_VISIBLE_DEVICES lists {len(ids)} device(s)")
+    return ids[local_rank]
+
+
 def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         raise SystemExit("usage: python -m nsdp_b200.launch <script.py> [args...]")
     local_rank = os.environ.get("LOCAL_RANK")
     if local_rank is not None and "NSDP_B200_KEEP_VISIBLE" not in os.environ:
-        os.environ["CUDA_VISIBLE_DEVICES"] = local_rank
+        os.environ["CUDA_VISIBLE_DEVICES"] = device_for_local_rank(int(local_rank), os.environ.get("CUDA_VISIBLE_DEVICES"))
     install_aliases()
     argv = rewrite_argv_for_rank(argv, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
                                  os.path.join(os.environ.get("TMPDIR", "/tmp"), f"nsdp_b200_launch_{os.getpid()}"))

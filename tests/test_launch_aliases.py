@@ -3,6 +3,8 @@ the mirrors (CPU-only check of the import plumbing)."""
 import importlib
 import sys
 
+import pytest
+
 
 def test_aliases_resolve_to_mirrors():
     saved = dict(sys.modules)
@@ -66,3 +68,12 @@ def test_resume_reads_rank0_checkpoints_on_every_rank(tmp_path):
     names = sorted(os.listdir(stale))
     assert names == ["model_00020", "modelbest_00010_0.123000", "opt_00020"]
     assert (stale / "model_00020").read_text() == "model_00020" and os.path.islink(stale / "opt_00020")
+
+
+def test_rank_device_is_taken_from_the_devices_the_job_was_given():
+    from nsdp_b200.launch import device_for_local_rank
+    assert device_for_local_rank(3, None) == "3" and device_for_local_rank(0, "") == "0"
+    assert device_for_local_rank(1, "4,5,6,7") == "5"                       # a job confined to the second half of the box
+    assert device_for_local_rank(0, "GPU-aaaa, GPU-bbbb") == "GPU-aaaa"
+    with pytest.raises(SystemExit):
+        device_for_local_rank(2, "0,1")
