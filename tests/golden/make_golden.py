@@ -10,7 +10,7 @@ from nsdp_b200/synth.py, so every consumer regenerates them bit-identically.
 The only part of the reference that cannot execute on a CPU is its CUDA-only FPS kernel
 (sampling.cpp:82-84); `pointnet2_ops._ext` is therefore shimmed with the C restatement in
 oracle/nsdp_oracle.c (which in turn is pinned against the real kernel on the GPU box,
-tests/test_gpu_ref_ext.py).
+tests/test_gpu_index_kernels.py, and on the CPU against the reference's own torch FPS, tests/test_index_golden.py).
 """
 import json
 import os
