@@ -3,7 +3,7 @@
 * On-disk samples: `surface_points.npz` / `flow.npz`-style archives with fp16 arrays `points` (and `normals`), read exactly
   like the reference's `dataset/utils.py:8-17` (`load_npz_surface_flow`, `load_npz_space_flow`: fp16 -> fp32).
 * Checkpoints: `model_%05d` / `opt_%05d` / `modelbest_%05d_%f` files holding `torch.save`d state_dicts, the names and the
-  resume rule of `utils/checkpoints.py:8-77` — files written by either implementation load in the other (the
+  resume rule of `utils/checkpoints.py:8-74` — files written by either implementation load in the other (the
   state_dict schema is identical, tests/test_schema.py).
 * `DeviceStager`: what `train.py:192-193` does with a blocking `.to(device)` per tensor on the compute stream —
   here the `default_collate`d dict of batch i+1 is copied from REUSED pinned host buffers on a side stream while
@@ -45,7 +45,7 @@ def save_npz_space_flow(path: str, points) -> None:
 
 
 # ---------------------------------------------------------------------------------------------------
-# checkpoints (utils/checkpoints.py:8-77)
+# checkpoints (utils/checkpoints.py:8-74)
 # ---------------------------------------------------------------------------------------------------
 def save_checkpoints(epoch: int, model, optimizer, experiment_directory: str) -> None:
     torch.save(model.state_dict(), os.path.join(experiment_directory, "model_{:05d}".format(epoch)))

@@ -1,4 +1,4 @@
-"""Interpolation decoder (reference: model/decoder/interpolation_decoder.py:7-100; the reference's ablation decoder,
+"""Interpolation decoder (reference: model/decoder/interpolation_decoder.py:8-88; the reference's ablation decoder,
 `decoder: interp`): Gaussian kernel regression of the anchor features at every query, then a ResNet-FC stack.
 
 Same constructor arguments, sub-module names (state_dict keys) and call signature as the reference. The kernel

@@ -1,4 +1,4 @@
-"""PointNet++-style encoder (reference: model/encoder/pointnetplusplus.py:5-100; the reference's ablation encoder,
+"""PointNet++-style encoder (reference: model/encoder/pointnetplusplus.py:5-96; the reference's ablation encoder,
 `encoder: pointnet++`) on the nsdp_b200 blocks.
 
 Same constructor arguments, sub-module names (hence state_dict keys) and returned dict as the reference. What runs
