@@ -39,3 +39,22 @@ def get_learning_rates(optimizer):
 
 def print_learning_rates(optimizer):
     print("".join(" | " + str(group["lr"]) for group in optimizer.param_groups))
+
+
+def weights_init(m):
+    """`model.apply(weights_init)`: Xavier-uniform weights and zero biases for convolutions and Linear layers, identity affine
+    for BatchNorm layers (model/learningrate.py:50-60)."""
+    import torch
+    if isinstance(m, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)):
+        torch.nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            torch.nn.init.zeros_(m.bias)
+    elif isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+        torch.nn.init.ones_(m.weight)
+        torch.nn.init.zeros_(m.bias)
+
+
+def clamp_gradient(model, clip):
+    """Clip every gradient element of `model` into [-clip, clip] (model/learningrate.py:62-64)."""
+    import torch
+    torch.nn.utils.clip_grad_value_(list(model.parameters()), clip)

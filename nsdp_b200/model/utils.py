@@ -33,3 +33,34 @@ def knn_indices(query: torch.Tensor, ref: torch.Tensor, k: int) -> torch.Tensor:
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     """Kept for API compatibility (model/utils.py:39-55); the hot path uses knn_indices instead."""
     return torch.sum((src[:, :, None] - dst[:, None]) ** 2, dim=-1)
+
+
+def farthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """The reference's torch-level FPS (model/utils.py:73-93), which its encoder keeps as a commented-out alternative to the
+    CUDA operator (model/encoder/blocks.py:283-284): RANDOM start index per shape, int64 indices (B, npoint), no skip rule.
+    Kept for API compatibility and off the hot path — the model calls ops.furthest_point_sampling (start 0, the
+    `pointnet2_ops` semantics). Runs on whatever device `xyz` lives on."""
+    B, N, _ = xyz.shape
+    picks = torch.zeros(B, npoint, dtype=torch.long, device=xyz.device)
+    nearest = torch.full((B, N), 1e10, dtype=xyz.dtype, device=xyz.device)     # squared distance to the closest pick so far
+    current = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+    rows = torch.arange(B, dtype=torch.long, device=xyz.device)
+    for i in range(npoint):
+        picks[:, i] = current
+        d = ((xyz - xyz[rows, current].view(B, 1, 3)) ** 2).sum(-1)
+        nearest = torch.where(d < nearest, d, nearest)
+        current = nearest.max(dim=-1)[1]
+    return picks
+
+
+def fibonacci_sphere(samples: int = 1):
+    """`samples` points spread evenly over the unit sphere by the golden-angle spiral, as a (samples, 3) float64 numpy array
+    (model/utils.py:13-36)."""
+    import math
+
+    import numpy as np
+    i = np.arange(samples, dtype=np.float64)
+    y = 1.0 - (i / float(samples - 1)) * 2.0 if samples > 1 else np.ones(1)
+    radius = np.sqrt(np.maximum(1.0 - y * y, 0.0))
+    theta = math.pi * (3.0 - math.sqrt(5.0)) * i
+    return np.stack([np.cos(theta) * radius, y, np.sin(theta) * radius], axis=1)
